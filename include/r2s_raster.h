@@ -1,0 +1,124 @@
+/*
+ * r2s_raster.h -- C ABI of the batched forward Gaussian-splat rasterizer with
+ * median depth.
+ *
+ * Stands in for the reference's CUDA rasterizer
+ *   third-party/diff-gaussian-rasterization-w-depth ("DGR", file:line relative to it)
+ *     CudaRasterizer::Rasterizer::forward     cuda_rasterizer/rasterizer.h:31-54,
+ *                                             cuda_rasterizer/rasterizer_impl.cu:198-341
+ *     CudaRasterizer::Rasterizer::markVisible cuda_rasterizer/rasterizer.h:24,
+ *                                             cuda_rasterizer/rasterizer_impl.cu:141-153
+ *   and its torch glue RasterizeGaussiansCUDA  rasterize_points.cu:35-117
+ * for B independent (scene, camera) views per call.  The Python class
+ * GaussianRasterizer of real2sim_eval_b200/rasterizer.py (same signature as
+ * diff_gaussian_rasterization/__init__.py:149-198) binds these entry points.
+ *
+ * Differences of mechanism (results are the reference's):
+ *   - no host synchronisation: the instance count stays on the device; the
+ *     caller sizes `max_instances` up front and may poll r2s_raster_status()
+ *     [reference: blocking cudaMemcpy of num_rendered, rasterizer_impl.cu:283-284];
+ *   - (tile, depth) ordering is produced by binning instances per tile and a
+ *     per-tile shared-memory sort on the unique key (depth bits, Gaussian id),
+ *     which is the order cub::DeviceRadixSort::SortPairs yields for the
+ *     reference's emission order [rasterizer_impl.cu:70-111, 303-311];
+ *   - tile ranges fall out of the binning scan [identifyTileRanges :116-138].
+ */
+#ifndef R2S_RASTER_H_
+#define R2S_RASTER_H_
+
+#include "r2s_common.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R2S_TILE 16 /* BLOCK_X = BLOCK_Y, cuda_rasterizer/config.h:15-17 */
+
+typedef struct r2s_raster_args {
+    int32_t B;               /* views in this call                                         */
+    int32_t views_per_scene; /* consecutive views sharing one Gaussian set (>= 1)          */
+    int32_t P;               /* Gaussians per scene                                        */
+    int32_t D, M;            /* active SH degree, SH coefficients per Gaussian             */
+    int32_t W, H;            /* image size (all views)                                     */
+    int32_t prefiltered;     /* accepted for signature parity; culled Gaussians are skipped */
+    float scale_modifier, tanfovx, tanfovy, z_threshold;
+    /* per scene: n_scenes = B / views_per_scene, leading dimension n_scenes */
+    const float* means3D;        /* [n_scenes,P,3]                              */
+    const float* scales;         /* [n_scenes,P,3] or NULL with cov3D_precomp   */
+    const float* rotations;      /* [n_scenes,P,4] wxyz, used un-normalised     */
+    const float* opacities;      /* [n_scenes,P]                                */
+    const float* shs;            /* [n_scenes,P,M,3] or NULL with colors_precomp */
+    const float* colors_precomp; /* [n_scenes,P,3] or NULL                      */
+    const float* cov3D_precomp;  /* [n_scenes,P,6] or NULL                      */
+    /* per view */
+    const float* viewmatrix; /* [B,16] column-major w2c (transform_utils.py:11)  */
+    const float* projmatrix; /* [B,16]                                           */
+    const float* campos;     /* [B,3]                                            */
+    const float* bg;         /* [3]                                              */
+    /* outputs (caller-owned) */
+    float* out_color; /* [B,3,H,W] */
+    float* out_depth; /* [B,1,H,W] */
+    int32_t* radii;   /* [B,P] or NULL */
+    /* scratch (caller-owned); size from r2s_raster_workspace_bytes */
+    void* workspace;
+    size_t workspace_bytes;
+    int64_t max_instances; /* capacity for (Gaussian, tile) instances over the whole batch */
+} r2s_raster_args;
+
+size_t r2s_raster_workspace_bytes(int32_t B, int32_t P, int32_t W, int32_t H, int64_t max_instances);
+
+/* Enqueue preprocess -> bin -> per-tile sort -> composite for all B views. */
+int r2s_raster_forward(const r2s_raster_args* args, void* stream);
+
+/* Blocking read-back of the device-side counters of the last forward on this
+ * workspace: total instances (the reference's num_rendered summed over views)
+ * and whether max_instances was exceeded (in which case the images hold only
+ * the background).  This is the only call that synchronises. */
+int r2s_raster_status(const void* workspace, void* stream, int64_t* num_rendered, int32_t* overflow);
+
+/* markVisible: present[i] = (view-space z > 0.01). [P] bool (1 byte each). */
+int r2s_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                     uint8_t* present, void* stream);
+
+/* Byte offsets of the intermediate arrays inside a workspace (for parity tests
+ * and for the algorithmic-bytes accounting in bench.py). */
+typedef struct r2s_raster_layout {
+    size_t status;       /* int64 total, int32 overflow, ...                         */
+    size_t depths;       /* float  [B*P]  view-space z                                */
+    size_t radii;        /* int32  [B*P]                                             */
+    size_t tiles_touched; /* uint32 [B*P]                                            */
+    size_t rec_a;        /* float4 [B*P] {x, y, conic.x, conic.y}                     */
+    size_t rec_b;        /* float4 [B*P] {conic.z, opacity, r, g}                     */
+    size_t rec_c;        /* float  [B*P] {b}                                          */
+    size_t tile_count;   /* uint32 [B*T]                                             */
+    size_t tile_offset;  /* uint32 [B*T+1] exclusive scan; ranges[t] = (off[t], off[t+1]) */
+    size_t tile_fill;    /* uint32 [B*T]                                             */
+    size_t keys;         /* uint64 [max_instances] sorted (depth bits << 32 | id) per tile */
+    size_t keys_alt;     /* uint64 [max_instances] merge scratch                      */
+    size_t total;        /* total bytes                                              */
+    int32_t tiles_x, tiles_y;
+} r2s_raster_layout;
+int r2s_raster_workspace_layout(int32_t B, int32_t P, int32_t W, int32_t H, int64_t max_instances,
+                                r2s_raster_layout* out);
+
+/* Per-stage device timing of r2s_raster_forward for the roofline report: when enabled,
+ * forward() records CUDA events between its kernels on the caller's stream (no sync);
+ * r2s_raster_get_profile synchronises on the last event and returns the milliseconds of
+ * {preprocess, scan, emit, tile_sort, composite} of the most recent forward. */
+#define R2S_RASTER_STAGES 5
+int r2s_raster_set_profile(int32_t enable);
+int r2s_raster_get_profile(float ms[R2S_RASTER_STAGES]);
+
+/* Translation-only skinning of the object Gaussians onto the particles (the stand-in for the
+ * reference's LBS step between physics and render, sim/renderer/gs_renderer.py:732-749 --
+ * SURVEY.md §8f row N1; rotations are NOT updated).  For env e and object Gaussian g:
+ *   means3D[e, g] = g0[g] + sum_k w[g,k] * (x4[e, idx[g,k]].xyz - x0[idx[g,k]])
+ * x4 is the physics state [E,N,4]; means3D is [E,P,3] (rows >= n_obj untouched). */
+int r2s_skin_translate(int32_t E, int32_t N, int32_t P, int32_t n_obj, int32_t K, const int32_t* idx,
+                       const float* w, const float* x4, const float* x0, const float* g0, float* means3D,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* R2S_RASTER_H_ */

@@ -1,0 +1,1073 @@
+// phys.cu -- batched PhysTwin spring-mass substep loop for sm_100a.
+//
+// What the reference runs as ~9 Warp kernels x num_substeps inside a CUDA graph
+// (sim/physics/spring_mass_warp.py:823-943, "SMW") runs here as ONE persistent
+// launch per frame: one CTA per environment, particle positions/velocities
+// resident in shared memory as float4 for every substep of the frame, spring
+// topology (shared by all environments) streamed from L2, per-environment rest
+// lengths streamed from HBM.  The force scatter with float atomics (SMW:103-104)
+// becomes an atomic-free gather over a per-particle adjacency list: the spring
+// force is exactly antisymmetric under endpoint swap, so the force on particle i
+// is the sum over its incident springs of F(x_i -> x_j).
+//
+// Kernel map (reference kernel -> here):
+//   eval_springs + update_vel_from_force   SMW:61-129   -> frame_kernel phase A
+//   object_collision (+loop)               SMW:132-268  -> frame_kernel phase B
+//   set_mesh_points / refit / zero forces  SMW:889-900  -> frame_kernel phase A prologue (warp 0/1)
+//   mesh_collision                         SMW:295-421  -> frame_kernel phase C
+//   integrate_ground_collision             SMW:424-474  -> frame_kernel phase C
+//   HashGrid.build + update_potential_collision / build_resting_collision_pairs
+//                                          SMW:196-227, 272-291 -> grid_kernel<false/true>
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "r2s_internal.h"
+#include "r2s_phys.h"
+
+namespace {
+
+// ------------------------------------------------------------------ vec3 helpers
+__device__ __forceinline__ float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
+__device__ __forceinline__ float3 operator+(float3 a, float3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ float3 operator-(float3 a, float3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float3 operator*(float3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ float3 operator/(float3 a, float s) { return f3(a.x / s, a.y / s, a.z / s); }
+__device__ __forceinline__ float dot3(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float len3(float3 a) { return sqrtf(dot3(a, a)); }
+__device__ __forceinline__ float3 cross3(float3 a, float3 b)
+{
+    return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
+}
+__device__ __forceinline__ float3 normalize3(float3 a)
+{
+    float l = len3(a);
+    return l > 0.0f ? a / l : f3(0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float clampf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ float3 xyz(float4 a) { return f3(a.x, a.y, a.z); }
+
+// ------------------------------------------------------------------ kernel params
+struct FrameParams {
+    int E, N, n_sub, has_self_collision, use_pusher, sign_mode;
+    int V, F, n_dyn, coll_cap, stage_dyn, smem_forces;
+    float dt, dashpot, drag_damping, rf, coll_dist;
+    float c_elas, c_fric, ce_elas, ce_fric, cs_elas, cs_fric;
+    const int* row_ptr;     // [N+1]
+    const int2* nbr_k;      // [nd] {neighbour, float bits of clamped stiffness (<0: inactive)}
+    const float* rest;      // [E or 1][nd]
+    long long rest_stride;  // nd or 0
+    const float* mass;      // [N]
+    const int* mask;        // [N]
+    float4* x4;             // [E][N]
+    float4* v4;             // [E][N]
+    float* vb_scratch;      // [E][3][N]  (only when state does not fit shared memory)
+    const int* coll_num;    // [E][N]
+    const int* coll_idx;    // [E][N][cap]
+    const int* status;      // [E][4]
+    const float* stat_verts;  // [V][3]  rest-pose vertices (dynamic ones are overridden per substep)
+    const int* faces;         // [F][3]
+    const int* mesh_map;      // [F]
+    const int* face_map;      // [F]
+    const float* interp_pts;  // [(E)][n_sub_table][n_dyn][3]
+    long long interp_stride;  // per env (0 = shared)
+    const float* interp_center;  // [(E)][n_sub_table][3]
+    long long center_stride;
+    const float* dyn_vel;  // [(E)][2][3]
+    long long dynvel_stride;
+    const float* dyn_omega;  // [(E)][3]
+    long long omega_stride;
+    float* coll_forces;  // [E][F][3]
+};
+
+// ------------------------------------------------------------------ mesh query
+struct MeshView {
+    const float* dyn;   // staged (shared) or table row (global): n_dyn x 3
+    const float* stat;  // global rest-pose vertices
+    const int* faces;
+    int n_dyn, F;
+    __device__ __forceinline__ float3 vert(int idx) const
+    {
+        const float* p = idx < n_dyn ? dyn + 3 * idx : stat + 3 * idx;
+        return f3(p[0], p[1], p[2]);
+    }
+};
+
+// Closest point on triangle (Ericson 5.1.5) as barycentrics (u, v):
+// point = u*a + v*b + (1-u-v)*c, the form wp.mesh_eval_position evaluates.
+__device__ __forceinline__ void closest_bary(float3 a, float3 b, float3 c, float3 p, float& u, float& v)
+{
+    float3 ab = b - a, ac = c - a, ap = p - a;
+    float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) { u = 1.0f; v = 0.0f; return; }
+    float3 bp = p - b;
+    float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) { u = 0.0f; v = 1.0f; return; }
+    float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        float t = d1 / (d1 - d3);
+        u = 1.0f - t; v = t; return;
+    }
+    float3 cp = p - c;
+    float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) { u = 0.0f; v = 0.0f; return; }
+    float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        float w = d2 / (d2 - d6);
+        u = 1.0f - w; v = 0.0f; return;
+    }
+    float va = d3 * d6 - d5 * d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        u = 0.0f; v = 1.0f - w; return;
+    }
+    float denom = 1.0f / (va + vb + vc);
+    float vv = vb * denom, ww = vc * denom;
+    u = 1.0f - vv - ww; v = vv;
+}
+
+__device__ __forceinline__ float solid_angle(float3 a, float3 b, float3 c, float3 p)
+{
+    a = a - p; b = b - p; c = c - p;
+    float la = len3(a), lb = len3(b), lc = len3(c);
+    float det = dot3(a, cross3(b, c));
+    float den = la * lb * lc + dot3(a, b) * lc + dot3(b, c) * la + dot3(c, a) * lb;
+    return 2.0f * atan2f(det, den);
+}
+
+// wp.mesh_query_point_sign_winding_number restated brute force (SMW:322-324):
+// strictly smaller squared distance from max_dist^2, faces in ascending index,
+// sign from the exact winding number against `threshold`.
+__device__ bool mesh_query(const MeshView& m, float3 p, float max_dist, float threshold,
+                           int sign_mode, int& face, float& u, float& v, float& sign)
+{
+    float best = max_dist * max_dist;
+    int hit = -1;
+    float bu = 0.f, bv = 0.f;
+    for (int fc = 0; fc < m.F; ++fc) {
+        const int* t = m.faces + 3 * fc;
+        float3 a = m.vert(t[0]), b = m.vert(t[1]), c = m.vert(t[2]);
+        float uu, vv;
+        closest_bary(a, b, c, p, uu, vv);
+        float3 q = a * uu + b * vv + c * (1.0f - uu - vv);
+        float3 d = q - p;
+        float d2 = dot3(d, d);
+        if (d2 < best) { best = d2; hit = fc; bu = uu; bv = vv; }
+    }
+    if (hit < 0) return false;
+    face = hit; u = bu; v = bv;
+    if (sign_mode == 1) { sign = 1.0f; return true; }
+    float total = 0.0f;
+    for (int fc = 0; fc < m.F; ++fc) {
+        const int* t = m.faces + 3 * fc;
+        total += solid_angle(m.vert(t[0]), m.vert(t[1]), m.vert(t[2]), p);
+    }
+    float wn = total * 0.25f * 0.31830988618379067f;
+    sign = (wn > threshold) ? -1.0f : 1.0f;
+    return true;
+}
+
+__device__ __forceinline__ float3 mesh_eval(const MeshView& m, int face, float u, float v)
+{
+    const int* t = m.faces + 3 * face;
+    return m.vert(t[0]) * u + m.vert(t[1]) * v + m.vert(t[2]) * (1.0f - u - v);
+}
+
+// ------------------------------------------------------------------ frame kernel
+// G = lanes cooperating on one particle's adjacency row in phase A.
+template <int G, bool kSmemState>
+__global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int nthreads = blockDim.x;
+    const int N = p.N;
+
+    // ---- carve shared memory
+    unsigned char* sp = smem_raw;
+    float4* sx;
+    float4* sv;
+    float* svb;  // [3][N]
+    if (kSmemState) {
+        sx = reinterpret_cast<float4*>(sp); sp += sizeof(float4) * N;
+        sv = reinterpret_cast<float4*>(sp); sp += sizeof(float4) * N;
+        svb = reinterpret_cast<float*>(sp); sp += sizeof(float) * 3 * ((N + 3) & ~3);
+    } else {
+        sx = p.x4 + (size_t)e * N;
+        sv = p.v4 + (size_t)e * N;
+        svb = p.vb_scratch + (size_t)e * 3 * N;
+    }
+    float* s_aabb = reinterpret_cast<float*>(sp); sp += sizeof(float) * 16;  // [0..5] dyn, [6..11] static
+    float* s_dyn = reinterpret_cast<float*>(sp);
+    if (p.stage_dyn) sp += sizeof(float) * 3 * ((p.n_dyn + 3) & ~3);
+    float* s_forces = reinterpret_cast<float*>(sp);
+    if (p.smem_forces) sp += sizeof(float) * 3 * p.F;
+
+    const bool has_mesh = p.F > 0;
+    const float dt = p.dt, rf = p.rf;
+    const float drag = expf(-dt * p.drag_damping);  // SMW:123
+
+    // ---- load state
+    if (kSmemState) {
+        const float4* gx = p.x4 + (size_t)e * N;
+        const float4* gv = p.v4 + (size_t)e * N;
+        for (int i = tid; i < N; i += nthreads) { sx[i] = gx[i]; sv[i] = gv[i]; }
+    }
+    // static part of the mesh bounding box (vertices n_dyn..V-1), once
+    if (has_mesh && tid < 32) {
+        float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+        for (int k = p.n_dyn + tid; k < p.V; k += 32)
+            for (int c = 0; c < 3; ++c) {
+                float q = p.stat_verts[3 * k + c];
+                lo[c] = fminf(lo[c], q); hi[c] = fmaxf(hi[c], q);
+            }
+        for (int c = 0; c < 3; ++c)
+            for (int o = 16; o > 0; o >>= 1) {
+                lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+                hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+            }
+        if (tid == 0)
+            for (int c = 0; c < 3; ++c) { s_aabb[6 + c] = lo[c]; s_aabb[9 + c] = hi[c]; }
+    }
+    const bool run_B = p.has_self_collision && p.status[4 * e] > 0;
+    const float* rest = p.rest + (size_t)e * p.rest_stride;
+    const float* g_interp = has_mesh ? p.interp_pts + (size_t)e * p.interp_stride : nullptr;
+    const float* g_center = has_mesh ? p.interp_center + (size_t)e * p.center_stride : nullptr;
+    const float* g_dynvel = has_mesh ? p.dyn_vel + (size_t)e * p.dynvel_stride : nullptr;
+    const float* g_omega = has_mesh ? p.dyn_omega + (size_t)e * p.omega_stride : nullptr;
+    float* g_forces = has_mesh ? p.coll_forces + (size_t)e * p.F * 3 : nullptr;
+    float* forces = p.smem_forces ? s_forces : g_forces;
+    __syncthreads();
+
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane_g = tid % G;
+    const int grp = tid / G;
+    const int n_groups = nthreads / G;
+    const unsigned gmask = (G == 32) ? kFull : (((1u << G) - 1u) << ((tid & 31) / G * G));
+
+    for (int step = 0; step < p.n_sub; ++step) {
+        // ============ phase A prologue: mesh vertices of this substep, force clear
+        if (has_mesh) {
+            const float* row = g_interp + (size_t)step * p.n_dyn * 3;
+            if (tid < 32) {  // SMW:889-899 set_mesh_points + refit (bounds)
+                float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+                for (int k = tid; k < p.n_dyn; k += 32)
+                    for (int c = 0; c < 3; ++c) {
+                        float q = row[3 * k + c];
+                        if (p.stage_dyn) s_dyn[3 * k + c] = q;
+                        lo[c] = fminf(lo[c], q); hi[c] = fmaxf(hi[c], q);
+                    }
+                for (int c = 0; c < 3; ++c)
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lo[c] = fminf(lo[c], __shfl_xor_sync(kFull, lo[c], o));
+                        hi[c] = fmaxf(hi[c], __shfl_xor_sync(kFull, hi[c], o));
+                    }
+                if (tid == 0)
+                    for (int c = 0; c < 3; ++c) { s_aabb[c] = lo[c]; s_aabb[3 + c] = hi[c]; }
+            } else if (tid < 64) {  // SMW:900 collision_forces.zero_()
+                for (int k = tid - 32; k < 3 * p.F; k += 32) forces[k] = 0.0f;
+            }
+        }
+        // ============ phase A: spring forces (gather) + velocity update -> svb
+        for (int i = grp; i < N; i += n_groups) {
+            const float4 xi4 = sx[i], vi4 = sv[i];
+            const float3 xi = xyz(xi4), vi = xyz(vi4);
+            const int beg = p.row_ptr[i], end = p.row_ptr[i + 1];
+            float3 acc = f3(0.f, 0.f, 0.f);
+            for (int k = beg + lane_g; k < end; k += G) {
+                const int2 nk = __ldg(p.nbr_k + k);
+                const float kk = __int_as_float(nk.y);
+                const float r = __ldg(rest + k);
+                if (kk >= 0.0f) {  // exp(Y) > Y_min guard (SMW:75), resolved at set_spring_Y time
+                    const float3 xj = xyz(sx[nk.x]), vj = xyz(sv[nk.x]);
+                    const float3 dis = xj - xi;
+                    const float dis_len = len3(dis);
+                    const float3 d = dis / fmaxf(dis_len, 1e-6f);
+                    const float3 spring_force = d * (kk * (dis_len / r - 1.0f));
+                    const float v_rel = dot3(vj - vi, d);
+                    const float3 dashpot = d * (p.dashpot * v_rel);
+                    acc = acc + (spring_force + dashpot);
+                }
+            }
+#pragma unroll
+            for (int o = G / 2; o > 0; o >>= 1) {
+                acc.x += __shfl_xor_sync(gmask, acc.x, o);
+                acc.y += __shfl_xor_sync(gmask, acc.y, o);
+                acc.z += __shfl_xor_sync(gmask, acc.z, o);
+            }
+            if (lane_g == 0) {  // SMW:107-129
+                const float m0 = p.mass[i];
+                const float3 g = f3(0.0f * m0, 0.0f * m0, -9.8f * m0) * rf;
+                const float3 all_force = acc + g;
+                const float3 a = all_force / m0;
+                const float3 v1 = vi + a * dt;
+                const float3 v2 = v1 * drag;
+                svb[i] = v2.x; svb[N + i] = v2.y; svb[2 * N + i] = v2.z;
+            }
+        }
+        __syncthreads();
+
+        // ============ phase B: self collision (SMW:132-193, 230-268): svb -> sv
+        if (run_B) {
+            const float ce = clampf(p.cs_elas, 0.0f, 1.0f);
+            const float cf = clampf(p.cs_fric, 0.0f, 2.0f);
+            const int* cnum = p.coll_num + (size_t)e * N;
+            const int* cidx = p.coll_idx + (size_t)e * N * p.coll_cap;
+            for (int i = tid; i < N; i += nthreads) {
+                const float3 x1 = xyz(sx[i]);
+                const float3 v1 = f3(svb[i], svb[N + i], svb[2 * N + i]);
+                const float m1 = p.mass[i];
+                const int mask1 = p.mask[i];
+                float valid = 0.0f;
+                float3 J_sum = f3(0.f, 0.f, 0.f);
+                const int cnt = cnum[i];
+                for (int k = 0; k < cnt; ++k) {
+                    const int j = cidx[(size_t)i * p.coll_cap + k];
+                    const float3 x2 = xyz(sx[j]);
+                    const float3 v2 = f3(svb[j], svb[N + j], svb[2 * N + j]);
+                    const float m2 = p.mass[j];
+                    const float3 dis = x2 - x1;
+                    const float dis_len = len3(dis);
+                    const float3 rel = v2 - v1;
+                    if (mask1 != p.mask[j] && dis_len < p.coll_dist && dot3(dis, rel) < -1e-4f) {
+                        valid += 1.0f;
+                        const float3 n = dis / fmaxf(dis_len, 1e-6f);
+                        const float3 v_rel_n = n * dot3(rel, n);
+                        const float inv_m = 1.0f / m1 + 1.0f / m2;
+                        const float3 impulse_n = (v_rel_n * (-(1.0f + ce))) / inv_m;
+                        const float v_rel_n_len = len3(v_rel_n);
+                        const float3 v_rel_t = rel - v_rel_n;
+                        const float v_rel_t_len = fmaxf(len3(v_rel_t), 1e-6f);
+                        const float a = fmaxf(0.0f, 1.0f - cf * (1.0f + ce) * v_rel_n_len / v_rel_t_len);
+                        const float3 impulse_t = (v_rel_t * (a - 1.0f)) / inv_m;
+                        J_sum = J_sum + (impulse_n + impulse_t);
+                    }
+                }
+                float3 vout = v1;
+                if (valid > 0.0f) {
+                    const float3 J_avg = J_sum / valid;
+                    vout = v1 - J_avg / m1;
+                }
+                sv[i] = make_float4(vout.x, vout.y, vout.z, 0.0f);
+            }
+            __syncthreads();
+        }
+
+        // ============ phase C: mesh collision (SMW:295-421) + ground (SMW:424-474)
+        MeshView mesh;
+        float3 box_lo = f3(0, 0, 0), box_hi = f3(0, 0, 0);
+        float3 c0 = f3(0, 0, 0), omega = f3(0, 0, 0), dv0 = f3(0, 0, 0), dv1 = f3(0, 0, 0);
+        if (has_mesh) {
+            mesh.dyn = p.stage_dyn ? s_dyn : g_interp + (size_t)step * p.n_dyn * 3;
+            mesh.stat = p.stat_verts; mesh.faces = p.faces; mesh.n_dyn = p.n_dyn; mesh.F = p.F;
+            // merged box of dynamic + static vertices, grown by max_dist (+ slack)
+            const float grow = 0.02f * 1.0001f + 1e-6f;
+            box_lo = f3(fminf(s_aabb[0], s_aabb[6]) - grow, fminf(s_aabb[1], s_aabb[7]) - grow,
+                        fminf(s_aabb[2], s_aabb[8]) - grow);
+            box_hi = f3(fmaxf(s_aabb[3], s_aabb[9]) + grow, fmaxf(s_aabb[4], s_aabb[10]) + grow,
+                        fmaxf(s_aabb[5], s_aabb[11]) + grow);
+            c0 = f3(g_center[3 * step], g_center[3 * step + 1], g_center[3 * step + 2]);
+            omega = f3(g_omega[0], g_omega[1], g_omega[2]);
+            dv0 = f3(g_dynvel[0], g_dynvel[1], g_dynvel[2]);
+            dv1 = f3(g_dynvel[3], g_dynvel[4], g_dynvel[5]);
+        }
+        for (int i = tid; i < N; i += nthreads) {
+            float3 x0 = xyz(sx[i]);
+            float3 v0 = run_B ? xyz(sv[i]) : f3(svb[i], svb[N + i], svb[2 * N + i]);
+            if (has_mesh) {
+                float3 next_x = x0 + v0 * dt;
+                float3 next_v = v0;
+                int face; float u, v, sign;
+                // the box test only skips queries that cannot hit (every triangle farther than max_dist)
+                const bool near_box = next_x.x >= box_lo.x && next_x.x <= box_hi.x && next_x.y >= box_lo.y &&
+                                      next_x.y <= box_hi.y && next_x.z >= box_lo.z && next_x.z <= box_hi.z;
+                if (near_box && mesh_query(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face, u, v, sign)) {
+                    int is_gripper;
+                    const int mm = p.mesh_map[face];
+                    if (!p.use_pusher) is_gripper = (mm == 0) ? 1 : ((mm == 1) ? 2 : 0);
+                    else is_gripper = (mm >= 0) ? 1 : 0;
+                    const float3 pc = mesh_eval(mesh, face, u, v);
+                    const float3 delta = next_x - pc;
+                    const float dist = len3(delta) * sign;
+                    const float margin = (is_gripper >= 1 && !p.use_pusher) ? 0.005f : 0.001f;
+                    const float err = dist - margin;
+                    if (err < 0.0f) {
+                        const float3 normal = normalize3(delta) * sign;
+                        float3 real_dyn = f3(0.f, 0.f, 0.f);
+                        float ce, cf;
+                        if (is_gripper >= 1) {
+                            const float3 rot = cross3(omega, x0 - c0);
+                            real_dyn = (is_gripper == 1 ? dv0 : dv1) + rot;
+                            v0 = v0 - real_dyn;
+                            ce = clampf(p.ce_elas, 0.0f, 1.0f);
+                            cf = clampf(p.ce_fric, 0.0f, 2.0f);
+                        } else {
+                            ce = clampf(p.c_elas, 0.0f, 1.0f);
+                            cf = clampf(p.c_fric, 0.0f, 2.0f);
+                        }
+                        const float3 v_normal = normal * dot3(v0, normal);
+                        const float3 v_tao = v0 - v_normal;
+                        const float v_normal_len = len3(v_normal);
+                        const float v_tao_len = fmaxf(len3(v_tao), 1e-6f);
+                        const float3 v_normal_new = v_normal * (-ce);
+                        const float a = fmaxf(0.0f, 1.0f - cf * (1.0f + ce) * v_normal_len / v_tao_len);
+                        const float3 v_tao_new = v_tao * a;
+                        next_v = v_normal_new + v_tao_new;
+                        if (is_gripper >= 1) next_v = next_v + real_dyn;
+                        if (is_gripper >= 1) {
+                            next_x = x0 + next_v * dt;
+                            int face2; float u2, v2, sign2;
+                            if (mesh_query(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face2, u2, v2, sign2)) {
+                                const float3 p2 = mesh_eval(mesh, face2, u2, v2);
+                                const float3 delta2 = next_x - p2;
+                                const float err2 = len3(delta2) * sign2 - margin;
+                                if (err2 < 0.0f) {
+                                    const float3 n2 = normalize3(delta2) * sign2;
+                                    next_x = next_x - n2 * err2;
+                                }
+                            }
+                        } else {
+                            next_x = next_x - normal * err;
+                        }
+                        const float3 dvn = (v_normal_new - v_normal) / dt;
+                        const int fm = p.face_map[face];
+                        atomicAdd(forces + 3 * fm, dvn.x);
+                        atomicAdd(forces + 3 * fm + 1, dvn.y);
+                        atomicAdd(forces + 3 * fm + 2, dvn.z);
+                    }
+                }
+                x0 = next_x;
+                v0 = next_v;
+            }
+            // integrate_ground_collision
+            const float x_z = x0.z, v_z = v0.z;
+            const float next_x_z = (x_z + v_z * dt) * rf;
+            float3 v1; float toi;
+            if (next_x_z < 0.0f && v_z * rf < -1e-4f) {
+                const float3 normal = f3(0.0f, 0.0f, 1.0f) * rf;
+                const float3 v_normal = normal * dot3(v0, normal);
+                const float3 v_tao = v0 - v_normal;
+                const float v_normal_len = len3(v_normal);
+                const float v_tao_len = fmaxf(len3(v_tao), 1e-6f);
+                const float ce = clampf(p.c_elas, 0.0f, 1.0f);
+                const float cf = clampf(p.c_fric, 0.0f, 2.0f);
+                const float3 v_normal_new = v_normal * (-ce);
+                const float a = fmaxf(0.0f, 1.0f - cf * (1.0f + ce) * v_normal_len / v_tao_len);
+                v1 = v_normal_new + v_tao * a;
+                toi = -(x_z - 0.0f) / v_z;
+            } else {
+                v1 = v0; toi = 0.0f;
+            }
+            const float3 xn = x0 + v0 * toi + v1 * (dt - toi);
+            sx[i] = make_float4(xn.x, xn.y, xn.z, 0.0f);
+            sv[i] = make_float4(v1.x, v1.y, v1.z, 0.0f);
+        }
+        __syncthreads();
+    }
+
+    // ---- write back
+    if (kSmemState) {
+        float4* gx = p.x4 + (size_t)e * N;
+        float4* gv = p.v4 + (size_t)e * N;
+        for (int i = tid; i < N; i += nthreads) { gx[i] = sx[i]; gv[i] = sv[i]; }
+    }
+    if (has_mesh && p.smem_forces)
+        for (int k = tid; k < 3 * p.F; k += nthreads) g_forces[k] = s_forces[k];
+}
+
+// ------------------------------------------------------------------ hash grid (Warp HashGrid restated)
+#define R2S_GRID_DIM 128
+__device__ __forceinline__ int grid_cell(int x, int y, int z)
+{
+    const int origin = 1 << 20;
+    x += origin; y += origin; z += origin;
+    x = max(0, x); y = max(0, y); z = max(0, z);
+    return (z % R2S_GRID_DIM) * (R2S_GRID_DIM * R2S_GRID_DIM) + (y % R2S_GRID_DIM) * R2S_GRID_DIM +
+           (x % R2S_GRID_DIM);
+}
+
+struct GridParams {
+    int E, N, npow2, cap, words;
+    float radius, coll_dist;
+    const float4* x4;
+    const int* mask;
+    unsigned* resting;              // [E or 1][N][words]
+    long long resting_stride;       // N*words or 0
+    int* coll_num;                  // [E][N]
+    int* coll_idx;                  // [E][N][cap]
+    int* status;                    // [E][4]
+    unsigned long long* key_scratch;  // [E][npow2] when keys do not fit shared memory, else null
+};
+
+// One CTA per environment: cell-sort the particles (bitonic on (cell, id) keys),
+// then run the Warp query loop per particle.  kResting: build_resting_collision_pairs
+// (SMW:272-291); else update_potential_collision (SMW:196-227).
+template <bool kResting>
+__global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int e = blockIdx.x, tid = threadIdx.x, nt = blockDim.x, N = p.N;
+    unsigned long long* keys = p.key_scratch ? p.key_scratch + (size_t)e * p.npow2
+                                             : reinterpret_cast<unsigned long long*>(smem_raw);
+    const float4* x4 = p.x4 + (size_t)e * N;
+    const float inv_w = 1.0f / p.radius;
+    for (int i = tid; i < p.npow2; i += nt) {
+        unsigned long long k = ~0ull;
+        if (i < N) {
+            const float4 q = x4[i];
+            const int c = grid_cell((int)(q.x * inv_w), (int)(q.y * inv_w), (int)(q.z * inv_w));
+            k = ((unsigned long long)(unsigned)c << 32) | (unsigned)i;
+        }
+        keys[i] = k;
+    }
+    if (!kResting && tid == 0) { p.status[4 * e] = 0; p.status[4 * e + 1] = 0; }
+    __syncthreads();
+    for (int k = 2; k <= p.npow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < p.npow2; i += nt) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], b = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { keys[i] = b; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    unsigned* resting = p.resting + (size_t)e * p.resting_stride;
+    int total = 0, overflow = 0;
+    for (int t = tid; t < N; t += nt) {
+        const int i = (int)(keys[t] & 0xffffffffu);  // wp.hash_grid_point_id: cell-sorted order
+        const float4 q = x4[i];
+        const float3 x1 = xyz(q);
+        const float r = p.radius;
+        const int xs = (int)((x1.x - r) * inv_w), ys = (int)((x1.y - r) * inv_w), zs = (int)((x1.z - r) * inv_w);
+        const int xe = min((int)((x1.x + r) * inv_w), xs + R2S_GRID_DIM - 1);
+        const int ye = min((int)((x1.y + r) * inv_w), ys + R2S_GRID_DIM - 1);
+        const int ze = min((int)((x1.z + r) * inv_w), zs + R2S_GRID_DIM - 1);
+        const int mask1 = p.mask[i];
+        int cnt = 0;
+        int* row = kResting ? nullptr : p.coll_idx + ((size_t)e * N + i) * p.cap;
+        for (int z = zs; z <= ze; ++z)
+            for (int y = ys; y <= ye; ++y)
+                for (int xx = xs; xx <= xe; ++xx) {
+                    const unsigned cell = (unsigned)grid_cell(xx, y, z);
+                    const unsigned long long lo_key = (unsigned long long)cell << 32;
+                    int lo = 0, hi = N;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        if (keys[mid] < lo_key) lo = mid + 1; else hi = mid;
+                    }
+                    for (; lo < N && (unsigned)(keys[lo] >> 32) == cell; ++lo) {
+                        const int j = (int)(keys[lo] & 0xffffffffu);
+                        if (kResting) {
+                            if (j < i) {
+                                atomicOr(resting + (size_t)i * p.words + (j >> 5), 1u << (j & 31));
+                                atomicOr(resting + (size_t)j * p.words + (i >> 5), 1u << (i & 31));
+                            }
+                        } else {
+                            if (j == i) continue;
+                            const bool rest_ij = (resting[(size_t)i * p.words + (j >> 5)] >> (j & 31)) & 1u;
+                            const bool rest_ji = (resting[(size_t)j * p.words + (i >> 5)] >> (i & 31)) & 1u;
+                            if (rest_ij || rest_ji) continue;
+                            const float3 dis = xyz(x4[j]) - x1;
+                            const float dis_len = len3(dis);
+                            if (mask1 != p.mask[j] && dis_len < p.coll_dist) {
+                                if (cnt < p.cap) row[cnt++] = j;
+                                else overflow++;
+                            }
+                        }
+                    }
+                }
+        if (!kResting) { p.coll_num[(size_t)e * N + i] = cnt; total += cnt; }
+    }
+    if (!kResting) {
+        if (total) atomicAdd(p.status + 4 * e, total);
+        if (overflow) atomicAdd(p.status + 4 * e + 1, overflow);
+    }
+}
+
+// ------------------------------------------------------------------ small utility kernels
+__global__ void pack_state_kernel(const float* __restrict__ src, long long stride_env, float4* __restrict__ dst,
+                                  int E, int N)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)E * N) return;
+    const int e = (int)(idx / N), i = (int)(idx % N);
+    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src) {
+        const float* s = src + (size_t)e * stride_env + 3 * (size_t)i;
+        o = make_float4(s[0], s[1], s[2], 0.f);
+    }
+    dst[idx] = o;
+}
+
+__global__ void unpack_state_kernel(const float4* __restrict__ src, float* __restrict__ dst, long long n)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n) return;
+    const float4 q = src[idx];
+    dst[3 * idx] = q.x; dst[3 * idx + 1] = q.y; dst[3 * idx + 2] = q.z;
+}
+
+// per directed entry: neighbour + clamped stiffness bits (negative = inactive), SMW:75,93
+__global__ void stiffness_kernel(const float* __restrict__ logY, const int* __restrict__ sid,
+                                 const int* __restrict__ nbr, float y_min, float y_max, int2* __restrict__ out,
+                                 int nd)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nd) return;
+    const float y = expf(logY[sid[k]]);
+    const float kk = (y > y_min) ? fminf(fmaxf(y, y_min), y_max) : -1.0f;
+    out[k] = make_int2(nbr[k], __float_as_int(kk));
+}
+
+__global__ void fill_kernel(float* p, float v, long long n)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) p[idx] = v;
+}
+__global__ void iota_kernel(int* p, int n)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < n) p[idx] = idx;
+}
+
+__global__ void rest_gather_kernel(const float* __restrict__ rest, long long rest_stride_env,
+                                   const int* __restrict__ sid, float* __restrict__ out, int n_env, int nd)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n_env * nd) return;
+    const int e = (int)(idx / nd), k = (int)(idx % nd);
+    out[idx] = rest[(size_t)e * rest_stride_env + sid[k]];
+}
+
+}  // namespace
+
+// ====================================================================== host side
+struct r2s_phys {
+    r2s_phys_desc d;
+    int nd = 0;  // directed adjacency entries (2S)
+    int threads = 1024;
+    int coll_cap = 64;
+    // device buffers
+    int* row_ptr = nullptr;
+    int* nbr = nullptr;
+    int* sid = nullptr;
+    int2* nbr_k = nullptr;
+    float* rest_csr = nullptr;
+    int rest_envs = 1;
+    float* logY = nullptr;
+    float* mass = nullptr;
+    int* mask = nullptr;
+    float4* x4 = nullptr;
+    float4* v4 = nullptr;
+    float* vb_scratch = nullptr;
+    int* coll_num = nullptr;
+    int* coll_idx = nullptr;
+    int* status = nullptr;
+    unsigned* resting = nullptr;
+    int words = 0;
+    unsigned long long* key_scratch = nullptr;
+    int npow2 = 0;
+    // mesh
+    int V = 0, F = 0, n_dyn = 0;
+    float* stat_verts = nullptr;
+    int* faces = nullptr;
+    int* mesh_map = nullptr;
+    int* face_map = nullptr;
+    float* coll_forces = nullptr;
+    float* interp_pts = nullptr;
+    float* interp_center = nullptr;
+    float* dyn_vel = nullptr;
+    float* dyn_omega = nullptr;
+    int motion_per_env = 0;
+    int motion_substeps = 0;
+    // launch config
+    bool smem_state = true;
+    size_t smem_bytes = 0;
+    int stage_dyn = 0, smem_forces = 0;
+    int max_smem_optin = 0;
+};
+
+namespace {
+
+template <typename T>
+int dmalloc(T** p, size_t n)
+{
+    *p = nullptr;
+    if (n == 0) n = 1;
+    R2S_CUDA_TRY(cudaMalloc((void**)p, n * sizeof(T)));
+    return R2S_OK;
+}
+
+int configure_launch(r2s_phys* h)
+{
+    const int N = h->d.N;
+    size_t misc = sizeof(float) * 16;
+    h->stage_dyn = 0;
+    h->smem_forces = 0;
+    if (h->F > 0) {
+        size_t dynb = sizeof(float) * 3 * ((h->n_dyn + 3) & ~3);
+        size_t fb = sizeof(float) * 3 * h->F;
+        if (dynb <= 24 * 1024) { h->stage_dyn = 1; misc += dynb; }
+        if (fb <= 24 * 1024) { h->smem_forces = 1; misc += fb; }
+    }
+    size_t state = sizeof(float4) * 2 * (size_t)N + sizeof(float) * 3 * ((N + 3) & ~3);
+    h->smem_state = state + misc + 256 <= (size_t)h->max_smem_optin;
+    h->smem_bytes = (h->smem_state ? state : 0) + misc + 64;
+    if (!h->smem_state && !h->vb_scratch)
+        if (int rc = dmalloc(&h->vb_scratch, (size_t)h->d.E * 3 * N)) return rc;
+    return R2S_OK;
+}
+
+template <int G>
+int launch_frame(r2s_phys* h, const FrameParams& fp, cudaStream_t st)
+{
+    if (h->smem_state) {
+        R2S_CUDA_TRY(cudaFuncSetAttribute(frame_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)h->smem_bytes));
+        frame_kernel<G, true><<<h->d.E, h->threads, h->smem_bytes, st>>>(fp);
+    } else {
+        R2S_CUDA_TRY(cudaFuncSetAttribute(frame_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)h->smem_bytes));
+        frame_kernel<G, false><<<h->d.E, h->threads, h->smem_bytes, st>>>(fp);
+    }
+    R2S_LAUNCH_CHECK();
+    return R2S_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+r2s_phys* r2s_phys_create(const r2s_phys_desc* desc)
+{
+    if (!desc || desc->E <= 0 || desc->N <= 0 || desc->S < 0 || !desc->springs || !desc->rest_lengths) {
+        r2s::set_error("r2s_phys_create: bad descriptor (E=%d N=%d S=%d)", desc ? desc->E : -1,
+                       desc ? desc->N : -1, desc ? desc->S : -1);
+        return nullptr;
+    }
+    r2s_phys* h = new r2s_phys();
+    h->d = *desc;
+    const int E = desc->E, N = desc->N, S = desc->S;
+    h->nd = 2 * S;
+    h->coll_cap = desc->coll_row_cap > 0 ? desc->coll_row_cap : 64;
+    h->threads = desc->threads > 0 ? desc->threads : 1024;
+    if (h->threads % 32 || h->threads > 1024) {
+        r2s::set_error("r2s_phys_create: threads must be a multiple of 32, <= 1024");
+        delete h;
+        return nullptr;
+    }
+    int dev = 0;
+    auto fail = [&](const char* what) -> r2s_phys* {
+        if (what) r2s::set_error("r2s_phys_create: %s", what);
+        r2s_phys_destroy(h);
+        return nullptr;
+    };
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess)
+        return fail("cannot query device");
+
+    // ---- adjacency (host): per particle, incident springs in ascending spring index
+    std::vector<int> springs(2 * (size_t)S);
+    if (S && cudaMemcpy(springs.data(), desc->springs, sizeof(int) * 2 * S, cudaMemcpyDeviceToHost) != cudaSuccess)
+        return fail("cannot read springs (must be a device pointer)");
+    std::vector<int> row_ptr(N + 1, 0), nbr(h->nd ? h->nd : 1), sid(h->nd ? h->nd : 1);
+    for (int t = 0; t < S; ++t) {
+        const int a = springs[2 * t], b = springs[2 * t + 1];
+        if (a < 0 || a >= N || b < 0 || b >= N) return fail("spring index out of range");
+        row_ptr[a + 1]++; row_ptr[b + 1]++;
+    }
+    for (int i = 0; i < N; ++i) row_ptr[i + 1] += row_ptr[i];
+    {
+        std::vector<int> cur(row_ptr.begin(), row_ptr.end() - 1);
+        for (int t = 0; t < S; ++t) {
+            const int a = springs[2 * t], b = springs[2 * t + 1];
+            nbr[cur[a]] = b; sid[cur[a]++] = t;
+            nbr[cur[b]] = a; sid[cur[b]++] = t;
+        }
+    }
+    bool ok = true;
+    ok &= dmalloc(&h->row_ptr, N + 1) == 0 && dmalloc(&h->nbr, h->nd) == 0 && dmalloc(&h->sid, h->nd) == 0 &&
+          dmalloc(&h->nbr_k, h->nd) == 0 && dmalloc(&h->logY, S) == 0 && dmalloc(&h->mass, N) == 0 &&
+          dmalloc(&h->mask, N) == 0 && dmalloc(&h->x4, (size_t)E * N) == 0 &&
+          dmalloc(&h->v4, (size_t)E * N) == 0 && dmalloc(&h->status, (size_t)E * 4) == 0;
+    if (!ok) return fail(nullptr);
+    cudaMemcpy(h->row_ptr, row_ptr.data(), sizeof(int) * (N + 1), cudaMemcpyHostToDevice);
+    if (h->nd) {
+        cudaMemcpy(h->nbr, nbr.data(), sizeof(int) * h->nd, cudaMemcpyHostToDevice);
+        cudaMemcpy(h->sid, sid.data(), sizeof(int) * h->nd, cudaMemcpyHostToDevice);
+    }
+    cudaMemset(h->status, 0, sizeof(int) * 4 * E);
+    cudaMemset(h->x4, 0, sizeof(float4) * (size_t)E * N);
+    cudaMemset(h->v4, 0, sizeof(float4) * (size_t)E * N);
+    if (desc->masses) cudaMemcpy(h->mass, desc->masses, sizeof(float) * N, cudaMemcpyDeviceToDevice);
+    else { fill_kernel<<<r2s::ceil_div(N, 256), 256>>>(h->mass, 1.0f, N); r2s::count_launch(); }
+    if (desc->collision_mask) cudaMemcpy(h->mask, desc->collision_mask, sizeof(int) * N, cudaMemcpyDeviceToDevice);
+    else { iota_kernel<<<r2s::ceil_div(N, 256), 256>>>(h->mask, N); r2s::count_launch(); }
+    if (desc->log_spring_Y) {
+        if (r2s_phys_set_spring_Y(h, desc->log_spring_Y, nullptr)) return fail(nullptr);
+    } else if (S) {
+        fill_kernel<<<r2s::ceil_div(S, 256), 256>>>(h->logY, logf(3e4f), S);
+        r2s::count_launch();
+        if (r2s_phys_set_spring_Y(h, h->logY, nullptr)) return fail(nullptr);
+    }
+    if (r2s_phys_set_rest_lengths(h, desc->rest_lengths, desc->rest_per_env, nullptr)) return fail(nullptr);
+
+    if (desc->self_collision) {
+        h->words = (N + 31) / 32;
+        h->npow2 = 1;
+        while (h->npow2 < N) h->npow2 <<= 1;
+        ok = dmalloc(&h->coll_num, (size_t)E * N) == 0 && dmalloc(&h->coll_idx, (size_t)E * N * h->coll_cap) == 0 &&
+             dmalloc(&h->resting, (size_t)E * N * h->words) == 0;
+        if (!ok) return fail(nullptr);
+        cudaMemset(h->coll_num, 0, sizeof(int) * (size_t)E * N);
+        cudaMemset(h->resting, 0, sizeof(unsigned) * (size_t)E * N * h->words);
+        if (sizeof(unsigned long long) * (size_t)h->npow2 > (size_t)h->max_smem_optin - 1024)
+            if (dmalloc(&h->key_scratch, (size_t)E * h->npow2)) return fail(nullptr);
+    }
+    if (configure_launch(h)) return fail(nullptr);
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail("device error during setup");
+    return h;
+}
+
+int r2s_phys_destroy(r2s_phys* h)
+{
+    if (!h) return R2S_OK;
+    void* ptrs[] = {h->row_ptr, h->nbr, h->sid, h->nbr_k, h->rest_csr, h->logY, h->mass, h->mask, h->x4, h->v4,
+                    h->vb_scratch, h->coll_num, h->coll_idx, h->status, h->resting, h->key_scratch,
+                    h->stat_verts, h->faces, h->mesh_map, h->face_map, h->coll_forces, h->interp_pts,
+                    h->interp_center, h->dyn_vel, h->dyn_omega};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    delete h;
+    return R2S_OK;
+}
+
+int r2s_phys_set_state(r2s_phys* h, const float* x, const float* v, int64_t stride, void* stream)
+{
+    R2S_REQUIRE(h && x, "r2s_phys_set_state: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)h->d.E * h->d.N;
+    pack_state_kernel<<<r2s::ceil_div(n, 256), 256, 0, st>>>(x, stride, h->x4, h->d.E, h->d.N);
+    R2S_LAUNCH_CHECK();
+    pack_state_kernel<<<r2s::ceil_div(n, 256), 256, 0, st>>>(v, stride, h->v4, h->d.E, h->d.N);
+    R2S_LAUNCH_CHECK();
+    return R2S_OK;
+}
+
+int r2s_phys_get_state(r2s_phys* h, float* x, float* v, void* stream)
+{
+    R2S_REQUIRE(h, "r2s_phys_get_state: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long n = (long long)h->d.E * h->d.N;
+    if (x) { unpack_state_kernel<<<r2s::ceil_div(n, 256), 256, 0, st>>>(h->x4, x, n); R2S_LAUNCH_CHECK(); }
+    if (v) { unpack_state_kernel<<<r2s::ceil_div(n, 256), 256, 0, st>>>(h->v4, v, n); R2S_LAUNCH_CHECK(); }
+    return R2S_OK;
+}
+
+int r2s_phys_set_spring_Y(r2s_phys* h, const float* logY, void* stream)
+{
+    R2S_REQUIRE(h && logY, "r2s_phys_set_spring_Y: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (h->d.S == 0) return R2S_OK;
+    if (logY != h->logY)
+        R2S_CUDA_TRY(cudaMemcpyAsync(h->logY, logY, sizeof(float) * h->d.S, cudaMemcpyDeviceToDevice, st));
+    stiffness_kernel<<<r2s::ceil_div(h->nd, 256), 256, 0, st>>>(h->logY, h->sid, h->nbr, h->d.spring_Y_min,
+                                                                h->d.spring_Y_max, h->nbr_k, h->nd);
+    R2S_LAUNCH_CHECK();
+    return R2S_OK;
+}
+
+int r2s_phys_set_rest_lengths(r2s_phys* h, const float* rest, int per_env, void* stream)
+{
+    R2S_REQUIRE(h && rest, "r2s_phys_set_rest_lengths: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int n_env = per_env ? h->d.E : 1;
+    if (!h->rest_csr || h->rest_envs != n_env) {
+        if (h->rest_csr) { cudaFree(h->rest_csr); h->rest_csr = nullptr; }
+        if (int rc = dmalloc(&h->rest_csr, (size_t)n_env * (h->nd ? h->nd : 1))) return rc;
+        h->rest_envs = n_env;
+    }
+    if (h->nd == 0) return R2S_OK;
+    const long long n = (long long)n_env * h->nd;
+    rest_gather_kernel<<<r2s::ceil_div(n, 256), 256, 0, st>>>(rest, h->d.S, h->sid, h->rest_csr, n_env, h->nd);
+    R2S_LAUNCH_CHECK();
+    return R2S_OK;
+}
+
+int r2s_phys_set_collide(r2s_phys* h, float elas, float fric, float eef_elas, float eef_fric, float self_elas,
+                         float self_fric)
+{
+    R2S_REQUIRE(h, "r2s_phys_set_collide: null handle");
+    if (elas == elas) h->d.collide_elas = elas;
+    if (fric == fric) h->d.collide_fric = fric;
+    if (eef_elas == eef_elas) h->d.collide_eef_elas = eef_elas;
+    if (eef_fric == eef_fric) h->d.collide_eef_fric = eef_fric;
+    if (self_elas == self_elas) h->d.collide_self_elas = self_elas;
+    if (self_fric == self_fric) h->d.collide_self_fric = self_fric;
+    return R2S_OK;
+}
+
+int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, const int32_t* mesh_map,
+                      const int32_t* face_map, int32_t V, int32_t F, int32_t n_dyn)
+{
+    R2S_REQUIRE(h && verts && faces && mesh_map && face_map, "r2s_phys_set_mesh: null argument");
+    R2S_REQUIRE(V > 0 && F > 0 && n_dyn >= 0 && n_dyn <= V, "r2s_phys_set_mesh: bad sizes V=%d F=%d n_dyn=%d", V, F,
+                n_dyn);
+    for (int k = 0; k < 3 * F; ++k)
+        R2S_REQUIRE(faces[k] >= 0 && faces[k] < V, "r2s_phys_set_mesh: face index out of range");
+    for (int k = 0; k < F; ++k)
+        R2S_REQUIRE(face_map[k] >= 0 && face_map[k] < F, "r2s_phys_set_mesh: face_map out of range");
+    void* old[] = {h->stat_verts, h->faces, h->mesh_map, h->face_map, h->coll_forces, h->interp_pts,
+                   h->interp_center, h->dyn_vel, h->dyn_omega};
+    for (void* p : old)
+        if (p) cudaFree(p);
+    h->interp_pts = h->interp_center = h->dyn_vel = h->dyn_omega = nullptr;
+    h->V = V; h->F = F; h->n_dyn = n_dyn;
+    const int E = h->d.E, ns = h->d.n_substeps;
+    if (dmalloc(&h->stat_verts, (size_t)3 * V) || dmalloc(&h->faces, (size_t)3 * F) || dmalloc(&h->mesh_map, F) ||
+        dmalloc(&h->face_map, F) || dmalloc(&h->coll_forces, (size_t)E * F * 3))
+        return R2S_ERR_CUDA;
+    R2S_CUDA_TRY(cudaMemcpy(h->stat_verts, verts, sizeof(float) * 3 * V, cudaMemcpyHostToDevice));
+    R2S_CUDA_TRY(cudaMemcpy(h->faces, faces, sizeof(int) * 3 * F, cudaMemcpyHostToDevice));
+    R2S_CUDA_TRY(cudaMemcpy(h->mesh_map, mesh_map, sizeof(int) * F, cudaMemcpyHostToDevice));
+    R2S_CUDA_TRY(cudaMemcpy(h->face_map, face_map, sizeof(int) * F, cudaMemcpyHostToDevice));
+    R2S_CUDA_TRY(cudaMemset(h->coll_forces, 0, sizeof(float) * (size_t)E * F * 3));
+    // SMW:699-711 defaults: rest pose repeated over the substeps, centre = mean, zero velocities
+    std::vector<float> tbl((size_t)ns * n_dyn * 3 + 1), ctr((size_t)ns * 3 + 1), zero(6, 0.f);
+    double c[3] = {0, 0, 0};
+    for (int k = 0; k < n_dyn; ++k)
+        for (int a = 0; a < 3; ++a) c[a] += verts[3 * k + a];
+    for (int s = 0; s < ns; ++s) {
+        if (n_dyn) memcpy(&tbl[(size_t)s * n_dyn * 3], verts, sizeof(float) * 3 * n_dyn);
+        for (int a = 0; a < 3; ++a) ctr[3 * s + a] = n_dyn ? (float)(c[a] / n_dyn) : 0.f;
+    }
+    if (dmalloc(&h->interp_pts, tbl.size()) || dmalloc(&h->interp_center, ctr.size()) || dmalloc(&h->dyn_vel, 6) ||
+        dmalloc(&h->dyn_omega, 3))
+        return R2S_ERR_CUDA;
+    R2S_CUDA_TRY(cudaMemcpy(h->interp_pts, tbl.data(), sizeof(float) * tbl.size(), cudaMemcpyHostToDevice));
+    R2S_CUDA_TRY(cudaMemcpy(h->interp_center, ctr.data(), sizeof(float) * ctr.size(), cudaMemcpyHostToDevice));
+    R2S_CUDA_TRY(cudaMemcpy(h->dyn_vel, zero.data(), sizeof(float) * 6, cudaMemcpyHostToDevice));
+    R2S_CUDA_TRY(cudaMemcpy(h->dyn_omega, zero.data(), sizeof(float) * 3, cudaMemcpyHostToDevice));
+    h->motion_per_env = 0;
+    h->motion_substeps = ns;
+    return configure_launch(h);
+}
+
+int r2s_phys_set_mesh_motion(r2s_phys* h, const float* interp_pts, const float* interp_center, const float* dyn_vel,
+                             const float* dyn_omega, int per_env, void* stream)
+{
+    R2S_REQUIRE(h && h->F > 0, "r2s_phys_set_mesh_motion: no mesh set");
+    R2S_REQUIRE(interp_pts && interp_center && dyn_vel && dyn_omega, "r2s_phys_set_mesh_motion: null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ne = per_env ? h->d.E : 1, ns = h->d.n_substeps;
+    if (h->motion_per_env != (per_env ? 1 : 0)) {
+        cudaFree(h->interp_pts); cudaFree(h->interp_center); cudaFree(h->dyn_vel); cudaFree(h->dyn_omega);
+        h->interp_pts = h->interp_center = h->dyn_vel = h->dyn_omega = nullptr;
+        if (dmalloc(&h->interp_pts, (size_t)ne * ns * h->n_dyn * 3) || dmalloc(&h->interp_center, (size_t)ne * ns * 3) ||
+            dmalloc(&h->dyn_vel, (size_t)ne * 6) || dmalloc(&h->dyn_omega, (size_t)ne * 3))
+            return R2S_ERR_CUDA;
+        h->motion_per_env = per_env ? 1 : 0;
+    }
+    const int nv = h->d.use_pusher ? 1 : 2;
+    R2S_CUDA_TRY(cudaMemcpyAsync(h->interp_pts, interp_pts, sizeof(float) * (size_t)ne * ns * h->n_dyn * 3,
+                                 cudaMemcpyDeviceToDevice, st));
+    R2S_CUDA_TRY(cudaMemcpyAsync(h->interp_center, interp_center, sizeof(float) * (size_t)ne * ns * 3,
+                                 cudaMemcpyDeviceToDevice, st));
+    if (nv == 2) {
+        R2S_CUDA_TRY(cudaMemcpyAsync(h->dyn_vel, dyn_vel, sizeof(float) * (size_t)ne * 6, cudaMemcpyDeviceToDevice, st));
+    } else {
+        R2S_CUDA_TRY(cudaMemcpy2DAsync(h->dyn_vel, sizeof(float) * 6, dyn_vel, sizeof(float) * 3, sizeof(float) * 3, ne,
+                                       cudaMemcpyDeviceToDevice, st));
+    }
+    R2S_CUDA_TRY(cudaMemcpyAsync(h->dyn_omega, dyn_omega, sizeof(float) * (size_t)ne * 3, cudaMemcpyDeviceToDevice, st));
+    return R2S_OK;
+}
+
+static int run_grid(r2s_phys* h, bool resting, cudaStream_t st)
+{
+    R2S_REQUIRE(h && h->d.self_collision, "self collision is disabled for this system");
+    GridParams g{};
+    g.E = h->d.E; g.N = h->d.N; g.npow2 = h->npow2; g.cap = h->coll_cap; g.words = h->words;
+    g.radius = h->d.collision_dist * 5.0f;
+    g.coll_dist = h->d.collision_dist;
+    g.x4 = h->x4; g.mask = h->mask; g.resting = h->resting; g.resting_stride = (long long)h->d.N * h->words;
+    g.coll_num = h->coll_num; g.coll_idx = h->coll_idx; g.status = h->status; g.key_scratch = h->key_scratch;
+    const size_t smem = h->key_scratch ? 0 : sizeof(unsigned long long) * (size_t)h->npow2;
+    if (resting) {
+        R2S_CUDA_TRY(cudaMemsetAsync(h->resting, 0, sizeof(unsigned) * (size_t)h->d.E * h->d.N * h->words, st));
+        R2S_CUDA_TRY(cudaFuncSetAttribute(grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grid_kernel<true><<<h->d.E, 1024, smem, st>>>(g);
+    } else {
+        R2S_CUDA_TRY(cudaFuncSetAttribute(grid_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        grid_kernel<false><<<h->d.E, 1024, smem, st>>>(g);
+    }
+    R2S_LAUNCH_CHECK();
+    return R2S_OK;
+}
+
+int r2s_phys_create_resting_case(r2s_phys* h, void* stream) { return run_grid(h, true, (cudaStream_t)stream); }
+int r2s_phys_update_collision_graph(r2s_phys* h, void* stream) { return run_grid(h, false, (cudaStream_t)stream); }
+
+int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
+{
+    R2S_REQUIRE(h, "r2s_phys_step: null handle");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ns = n_substeps > 0 ? n_substeps : h->d.n_substeps;
+    R2S_REQUIRE(h->F == 0 || ns <= h->d.n_substeps,
+                "r2s_phys_step: %d substeps exceed the mesh motion table (%d rows)", ns, h->d.n_substeps);
+    FrameParams p{};
+    p.E = h->d.E; p.N = h->d.N; p.n_sub = ns;
+    p.has_self_collision = h->d.self_collision; p.use_pusher = h->d.use_pusher; p.sign_mode = h->d.sign_mode;
+    p.V = h->V; p.F = h->F; p.n_dyn = h->n_dyn; p.coll_cap = h->coll_cap;
+    p.stage_dyn = h->stage_dyn; p.smem_forces = h->smem_forces;
+    p.dt = h->d.dt; p.dashpot = h->d.dashpot_damping; p.drag_damping = h->d.drag_damping;
+    p.rf = h->d.reverse_z ? -1.0f : 1.0f; p.coll_dist = h->d.collision_dist;
+    p.c_elas = h->d.collide_elas; p.c_fric = h->d.collide_fric;
+    p.ce_elas = h->d.collide_eef_elas; p.ce_fric = h->d.collide_eef_fric;
+    p.cs_elas = h->d.collide_self_elas; p.cs_fric = h->d.collide_self_fric;
+    p.row_ptr = h->row_ptr; p.nbr_k = h->nbr_k; p.rest = h->rest_csr;
+    p.rest_stride = h->rest_envs > 1 ? h->nd : 0;
+    p.mass = h->mass; p.mask = h->mask; p.x4 = h->x4; p.v4 = h->v4; p.vb_scratch = h->vb_scratch;
+    p.coll_num = h->coll_num; p.coll_idx = h->coll_idx; p.status = h->status;
+    p.stat_verts = h->stat_verts; p.faces = h->faces; p.mesh_map = h->mesh_map; p.face_map = h->face_map;
+    p.interp_pts = h->interp_pts; p.interp_center = h->interp_center; p.dyn_vel = h->dyn_vel; p.dyn_omega = h->dyn_omega;
+    const long long pe = h->motion_per_env ? 1 : 0;
+    p.interp_stride = pe * h->d.n_substeps * h->n_dyn * 3;
+    p.center_stride = pe * h->d.n_substeps * 3;
+    p.dynvel_stride = pe * 6;
+    p.omega_stride = pe * 3;
+    p.coll_forces = h->coll_forces;
+    return launch_frame<8>(h, p, st);
+}
+
+int r2s_phys_get_ptrs(r2s_phys* h, r2s_phys_ptrs* out)
+{
+    R2S_REQUIRE(h && out, "r2s_phys_get_ptrs: null argument");
+    out->x4 = reinterpret_cast<float*>(h->x4);
+    out->v4 = reinterpret_cast<float*>(h->v4);
+    out->collision_forces = h->coll_forces;
+    out->mesh_map = h->mesh_map;
+    out->coll_num = h->coll_num;
+    out->coll_idx = h->coll_idx;
+    out->status = h->status;
+    out->F = h->F;
+    out->coll_row_cap = h->coll_cap;
+    out->smem_state = h->smem_state ? 1 : 0;
+    out->smem_bytes = (int32_t)h->smem_bytes;
+    return R2S_OK;
+}
+
+int64_t r2s_phys_algorithmic_bytes(const r2s_phys* h)
+{
+    return h ? 52ll * h->d.N + 16ll * h->d.S : 0;
+}
+
+}  // extern "C"

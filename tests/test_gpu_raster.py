@@ -1,0 +1,315 @@
+"""GPU parity: CUDA rasterizer (through the C ABI) vs the CPU oracle
+(oracle/raster_ref.c), vs the UNMODIFIED reference CUDA rasterizer when
+oracle/_ref/libref_raster.so travelled with the snapshot, and vs the committed
+golden fixtures made from that reference (tests/golden/raster_*.npz).
+
+Contract (BASELINE.json north_star): RGB / depth within 1e-4 relative per pixel.
+Integer stages (radii, tile ranges, sorted instance lists) are compared bit-exactly
+whenever the float stage feeding them agrees bit-exactly, which the tests check
+first.  Per-pixel thresholds (alpha < 1/255, T < 1e-4, the median-depth crossing)
+turn 1-ulp differences in exp() into isolated jumps, so image comparisons allow a
+small counted budget of outlier pixels and say so."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import r2s_testutil as _util
+from real2sim_eval_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-4
+ATOL = 1e-5
+OUTLIER_FRAC = 2e-3   # pixels allowed to differ by a threshold flip
+
+
+def _torchify(d, dev="cuda"):
+    import torch
+    return {k: torch.tensor(v, device=dev) for k, v in d.items()}
+
+
+def _run_cuda(g, cam, sh_degree=0, bg=(0.0, 0.0, 0.0), **kw):
+    import torch
+    from real2sim_eval_b200.rasterizer import BatchedRasterizer
+    r = BatchedRasterizer("cuda")
+    t = _torchify(g)
+    kw.setdefault("max_instances", 64 * len(g["means3D"]) + 4096)
+    color, radii, depth = r.forward(
+        t["means3D"], t["opacities"], viewmatrix=torch.tensor(cam.view).cuda(), projmatrix=torch.tensor(cam.proj).cuda(),
+        campos=torch.tensor(cam.campos).cuda(), bg=torch.tensor(bg, dtype=torch.float32).cuda(), W=cam.W, H=cam.H,
+        tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, shs=t.get("shs"), colors_precomp=t.get("colors_precomp"),
+        scales=t.get("scales"), rotations=t.get("rotations"), cov3D_precomp=t.get("cov3D_precomp"),
+        sh_degree=sh_degree, z_threshold=cam.z_threshold, **kw)
+    total, overflow = r.status()
+    return r, color[0].cpu().numpy(), radii[0].cpu().numpy(), depth[0].cpu().numpy(), total, overflow
+
+
+def _run_oracle(g, cam, sh_degree=0, bg=(0.0, 0.0, 0.0), aux=True):
+    from oracle import raster_ref
+    return raster_ref.rasterize(
+        g["means3D"], g["opacities"], viewmatrix=cam.view, projmatrix=cam.proj, campos=cam.campos,
+        bg=np.asarray(bg, np.float32), W=cam.W, H=cam.H, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, shs=g.get("shs"),
+        colors_precomp=g.get("colors_precomp"), scales=g.get("scales"), rotations=g.get("rotations"),
+        cov3D_precomp=g.get("cov3D_precomp"), sh_degree=sh_degree, z_threshold=cam.z_threshold, aux=aux)
+
+
+def _close_images(a, b, what):
+    bad = np.abs(a - b) > (ATOL + RTOL * np.abs(b))
+    frac = bad.mean()
+    assert frac <= OUTLIER_FRAC, f"{what}: {bad.sum()} of {bad.size} pixels beyond rtol={RTOL} (max |d|={np.abs(a - b).max()})"
+    return frac
+
+
+def _sorted_lists(r, P):
+    """(ranges [T,2], list of per-tile id arrays) from the CUDA workspace, view 0."""
+    it = r.intermediates()
+    off = it["tile_offset"].cpu().numpy().astype(np.int64)
+    T = it["tiles"][0] * it["tiles"][1]
+    keys = it["keys"].cpu().numpy().view(np.uint64)
+    return off[:T + 1], keys
+
+
+@pytest.mark.parametrize("W,H,P,seed", [(64, 64, 1500, 1), (128, 96, 4000, 2), (200, 120, 2500, 3)])
+def test_matches_oracle_stagewise(W, H, P, seed):
+    g = _util.small_gaussians(seed, P)
+    cam = _util.make_test_camera(W, H)
+    r, color, radii, depth, total, overflow = _run_cuda(g, cam, bg=(0.1, 0.2, 0.3))
+    oc, orad, od, aux = _run_oracle(g, cam, bg=(0.1, 0.2, 0.3))
+    assert not overflow
+    it = r.intermediates()
+    # --- preprocess: float stage within a few ulp, integer stage exact wherever floats agree
+    depths = it["depths"][0].cpu().numpy()
+    assert np.allclose(depths, aux["depths"], rtol=2e-6, atol=1e-7)
+    vis = orad > 0
+    same_vis = (radii > 0) == vis
+    assert same_vis.mean() > 0.999
+    ra = it["rec_a"][0].cpu().numpy()
+    assert np.allclose(ra[vis & same_vis, :2], aux["means2D"][vis & same_vis], rtol=1e-5, atol=2e-4)
+    agree = same_vis & (radii == orad)
+    assert agree.mean() > 0.995, "radii (ceil of 3 sigma) may flip only on exact ties"
+    tt = it["tiles_touched"][0].cpu().numpy().astype(np.int64)
+    assert (tt[agree] == aux["tiles_touched"][agree].astype(np.int64)).mean() > 0.999
+    # --- binning + sort: exact when the float stage agreed exactly
+    float_exact = np.array_equal(depths, aux["depths"]) and np.array_equal(radii, orad) and \
+        np.array_equal(tt, aux["tiles_touched"].astype(np.int64)) and \
+        np.array_equal(ra[vis, :2], aux["means2D"][vis])
+    off, keys = _sorted_lists(r, P)
+    assert total == off[-1]
+    for t in range(len(off) - 1):      # every tile list is sorted by (depth bits, id)
+        seg = keys[off[t]:off[t + 1]]
+        assert (np.diff(seg.astype(np.uint64).view(np.int64)) > 0).all()
+    if float_exact:
+        assert total == aux["num_rendered"]
+        assert np.array_equal(np.stack([off[:-1], off[1:]], 1)[aux["ranges"][:, 1] > aux["ranges"][:, 0]],
+                              aux["ranges"][aux["ranges"][:, 1] > aux["ranges"][:, 0]].astype(np.int64))
+        assert np.array_equal((keys[:total] & np.uint64(0xffffffff)).astype(np.uint32), aux["point_list"])
+    # --- images
+    _close_images(color, oc, "color vs oracle")
+    _close_images(depth, od, "depth vs oracle")
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3])
+def test_sh_degrees_and_precomputed_inputs(deg):
+    P, M = 800, (deg + 1) ** 2
+    g = _util.small_gaussians(10 + deg, P, sh_coeffs=M)
+    cam = _util.make_test_camera(96, 64)
+    _, color, radii, depth, _, _ = _run_cuda(g, cam, sh_degree=deg)
+    oc, orad, od, aux = _run_oracle(g, cam, sh_degree=deg)
+    _close_images(color, oc, f"SH degree {deg}")
+    # precomputed colour + covariance path (colors_precomp / cov3D_precomp)
+    g2 = dict(means3D=g["means3D"], opacities=g["opacities"], colors_precomp=aux["rgb"], cov3D_precomp=aux["cov3D"])
+    _, color2, radii2, depth2, _, _ = _run_cuda(g2, cam)
+    oc2, orad2, od2, _ = _run_oracle(g2, cam)
+    _close_images(color2, oc2, "precomputed inputs")
+    assert (radii2 == orad2).mean() > 0.995
+
+
+def test_argument_errors_match_reference_messages():
+    import torch
+    from real2sim_eval_b200.rasterizer import GaussianRasterizer, GaussianRasterizationSettings
+    cam = _util.make_test_camera(32, 32)
+    t = lambda a: torch.tensor(a).cuda()
+    rs = GaussianRasterizationSettings(32, 32, cam.tanfovx, cam.tanfovy, t(np.zeros(3, np.float32)), 1.0,
+                                       t(cam.view).reshape(1, 4, 4), t(cam.proj).reshape(1, 4, 4), 0, t(cam.campos),
+                                       False, 0.05)
+    g = _torchify(_util.small_gaussians(5, 50))
+    rast = GaussianRasterizer(rs)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(means3D=g["means3D"], means2D=None, opacities=g["opacities"], scales=g["scales"], rotations=g["rotations"])
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        rast(means3D=g["means3D"], means2D=None, opacities=g["opacities"], shs=g["shs"])
+    color, radii, depth = rast(means3D=g["means3D"], means2D=torch.zeros_like(g["means3D"]), opacities=g["opacities"],
+                               shs=g["shs"], scales=g["scales"], rotations=g["rotations"])
+    assert tuple(color.shape) == (3, 32, 32) and tuple(depth.shape) == (1, 32, 32) and radii.dtype == torch.int32
+    vis = rast.markVisible(g["means3D"])
+    from oracle import raster_ref
+    assert np.array_equal(vis.cpu().numpy(), raster_ref.mark_visible(g["means3D"].cpu().numpy(), cam.view, cam.proj))
+
+
+def test_empty_and_fully_culled_inputs():
+    cam = _util.make_test_camera(48, 40)
+    g = _util.small_gaussians(3, 64)
+    g["means3D"][:] += np.array([5.0, 0.0, 0.0], np.float32)  # behind the camera
+    _, color, radii, depth, total, _ = _run_cuda(g, cam, bg=(0.25, 0.5, 0.75))
+    assert total == 0 and (radii == 0).all()
+    assert np.allclose(color, np.array([0.25, 0.5, 0.75], np.float32)[:, None, None]) and (depth == 15.0).all()
+    import torch
+    from real2sim_eval_b200.rasterizer import BatchedRasterizer
+    r = BatchedRasterizer("cuda")
+    z = lambda *s: torch.zeros(*s, device="cuda")
+    color, radii, depth = r.forward(z(0, 3), z(0, 1), viewmatrix=torch.tensor(cam.view).cuda(),
+                                    projmatrix=torch.tensor(cam.proj).cuda(), campos=torch.tensor(cam.campos).cuda(),
+                                    bg=z(3), W=48, H=40, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, shs=z(0, 1, 3),
+                                    scales=z(0, 3), rotations=z(0, 4))
+    assert float(color.abs().max()) == 0.0 and float(depth.min()) == 15.0
+
+
+def test_overflow_is_reported_and_dropin_regrows():
+    import torch
+    from real2sim_eval_b200.rasterizer import BatchedRasterizer, GaussianRasterizer, GaussianRasterizationSettings
+    g = _util.small_gaussians(7, 3000, scale=0.05)
+    cam = _util.make_test_camera(96, 96)
+    r, color, _, _, total, overflow = _run_cuda(g, cam, bg=(1.0, 0.0, 0.0), max_instances=100)
+    assert overflow and total > 100
+    assert np.allclose(color[0], 1.0) and np.allclose(color[1:], 0.0), "overflow renders background only"
+    # the drop-in path notices the overflow of its default workspace and re-runs with room
+    t = lambda a: torch.tensor(a).cuda()
+    rs = GaussianRasterizationSettings(96, 96, cam.tanfovx, cam.tanfovy, t(np.zeros(3, np.float32)), 1.0, t(cam.view),
+                                       t(cam.proj), 0, t(cam.campos), False, cam.z_threshold)
+    tg = _torchify(g)
+    color, radii, depth = GaussianRasterizer(rs)(means3D=tg["means3D"], means2D=None, opacities=tg["opacities"],
+                                                 shs=tg["shs"], scales=tg["scales"], rotations=tg["rotations"])
+    oc, _, od, _ = _run_oracle(g, cam)
+    _close_images(color.cpu().numpy(), oc, "drop-in after regrow")
+
+
+def test_long_tile_lists_take_the_merge_path():
+    """> 4096 instances in one tile: chunked shared-memory sort + merge-path passes."""
+    g = _util.small_gaussians(11, 12000, box=((-0.05, -0.05, 0.1), (0.05, 0.05, 0.2)), scale=0.01)
+    cam = _util.make_test_camera(32, 32)
+    r, color, radii, depth, total, overflow = _run_cuda(g, cam, max_instances=200000)
+    oc, orad, od, aux = _run_oracle(g, cam)
+    off, keys = _sorted_lists(r, 12000)
+    assert np.diff(off).max() > 4096, "scenario must exceed one shared-memory chunk"
+    for t in range(len(off) - 1):
+        seg = keys[off[t]:off[t + 1]]
+        assert (np.diff(seg.view(np.int64)) > 0).all()
+    _close_images(color, oc, "long lists")
+    _close_images(depth, od, "long lists depth")
+
+
+def test_batch_equals_single_views_and_shared_scene():
+    """B views in one enqueue == B separate calls (bitwise); views_per_scene shares Gaussians."""
+    import torch
+    from real2sim_eval_b200.rasterizer import BatchedRasterizer
+    W, H, P = 80, 48, 1200
+    cams = [_util.make_test_camera(W, H, eye=(0.9, 0.05 + 0.1 * i, 0.5)) for i in range(4)]
+    gs = [_util.small_gaussians(20 + s, P) for s in range(2)]           # 2 scenes x 2 cameras
+    singles = []
+    for b, cam in enumerate(cams):
+        _, color, radii, depth, _, _ = _run_cuda(gs[b // 2], cam)
+        singles.append((color, radii, depth))
+    r = BatchedRasterizer("cuda")
+    st = lambda key: torch.tensor(np.stack([g[key] for g in gs])).cuda()
+    color, radii, depth = r.forward(
+        st("means3D"), st("opacities"), viewmatrix=torch.tensor(np.stack([c.view for c in cams])).cuda(),
+        projmatrix=torch.tensor(np.stack([c.proj for c in cams])).cuda(),
+        campos=torch.tensor(np.stack([c.campos for c in cams])).cuda(), bg=torch.zeros(3).cuda(), W=W, H=H,
+        tanfovx=cams[0].tanfovx, tanfovy=cams[0].tanfovy, shs=st("shs"), scales=st("scales"), rotations=st("rotations"),
+        views_per_scene=2)
+    for b in range(4):
+        assert np.array_equal(color[b].cpu().numpy(), singles[b][0])
+        assert np.array_equal(radii[b].cpu().numpy(), singles[b][1])
+        assert np.array_equal(depth[b].cpu().numpy(), singles[b][2])
+
+
+def test_known_answers_single_gaussian():
+    """Centre pixel alpha = min(0.99, opacity) (forward.cu:350) and the median depth rule."""
+    import torch
+    cam = _util.make_test_camera(33, 33, eye=(1.0, 0.0, 0.0), target=(0.0, 0.0, 0.0))
+    g = dict(means3D=np.zeros((1, 3), np.float32), scales=np.full((1, 3), 0.05, np.float32),
+             rotations=np.array([[1, 0, 0, 0]], np.float32), opacities=np.array([[0.6]], np.float32),
+             colors_precomp=np.array([[1.0, 0.5, 0.25]], np.float32))
+    _, color, radii, depth, total, _ = _run_cuda(g, cam)
+    oc, _, od, aux = _run_oracle(g, cam)
+    cx, cy = np.round(aux["means2D"][0]).astype(int)
+    # the projected centre is within half a pixel of (cx, cy): alpha there is opacity * exp(-small)
+    assert 0.55 < color[0, cy, cx] <= 0.6 and abs(color[1, cy, cx] - 0.5 * color[0, cy, cx]) < 1e-6
+    assert color.max() <= 0.6 + 1e-6
+    assert depth[0, cy, cx] == np.float32(aux["depths"][0]), "T crosses 0.5 at this Gaussian -> its depth"
+    assert depth[0, 0, 0] == 15.0
+    _close_images(color, oc, "single gaussian")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libref_raster.so")),
+                    reason="oracle/_ref not built (needs /root/reference at build time)")
+@pytest.mark.parametrize("W,H,P,seed,deg", [(64, 64, 2000, 1, 0), (160, 96, 6000, 4, 0), (96, 96, 1500, 5, 2)])
+def test_matches_unmodified_reference_cuda(W, H, P, seed, deg):
+    """Live comparison with the reference's own CUDA rasterizer on the same device."""
+    import ref_raster
+    g = _util.small_gaussians(seed, P, sh_coeffs=(deg + 1) ** 2)
+    cam = _util.make_test_camera(W, H)
+    rc, rr, rd, n = ref_raster.forward(g, cam, sh_degree=deg, bg=(0.1, 0.2, 0.3))
+    _, color, radii, depth, total, _ = _run_cuda(g, cam, sh_degree=deg, bg=(0.1, 0.2, 0.3))
+    assert total == n, "instance count equals the reference's num_rendered"
+    assert np.array_equal(radii, rr)
+    fc = _close_images(color, rc, "color vs reference CUDA")
+    fd = _close_images(depth, rd, "depth vs reference CUDA")
+    # pin the CPU oracle against the real reference.  The oracle evaluates without FMA contraction,
+    # the reference with it: a Gaussian whose 3-sigma radius sits on an integer can round the other
+    # way (ceil), which changes its tile rectangle and touches a few hundred pixels by < 1e-2.
+    oc, orad, od, _ = _run_oracle(g, cam, sh_degree=deg, bg=(0.1, 0.2, 0.3))
+    assert (orad == rr).mean() >= 0.995
+    bad = np.abs(oc - rc) > (ATOL + RTOL * np.abs(rc))
+    assert bad.mean() <= 0.05 and np.abs(oc - rc).max() <= 2e-2, (bad.mean(), np.abs(oc - rc).max())
+
+
+def test_golden_fixtures_from_reference():
+    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "raster_*.npz")))
+    if not files:
+        pytest.skip("golden fixtures not generated yet (tests/golden/make_raster_golden.py on a GPU box)")
+    for f in files:
+        d = np.load(f)
+        g = {k: d[k] for k in ("means3D", "scales", "rotations", "opacities", "shs")}
+        cam = synth.Camera(int(d["W"]), int(d["H"]), float(d["tanfovx"]), float(d["tanfovy"]), d["view"], d["proj"],
+                           d["campos"], float(d["z_threshold"]))
+        _, color, radii, depth, total, _ = _run_cuda(g, cam, sh_degree=int(d["sh_degree"]), bg=tuple(d["bg"]))
+        assert total == int(d["num_rendered"])
+        assert np.array_equal(radii, d["radii"])
+        _close_images(color, d["color"], f"{os.path.basename(f)} color")
+        _close_images(depth, d["depth"], f"{os.path.basename(f)} depth")
+
+
+def test_full_size_properties_512():
+    """BASELINE config 2 render size (512x512, 200k Gaussians/scene), 4 views: properties that need no
+    oracle at this size -- per-tile lists sorted, instance totals consistent, colours in range,
+    a permutation of the Gaussian order leaves the image unchanged up to depth ties."""
+    import torch
+    from real2sim_eval_b200.rasterizer import BatchedRasterizer
+    P, W, H, B = 200_000, 512, 512, 4
+    rope = synth.make_rope()
+    gs = [synth.make_gaussians(1234 + e, P, rope.x) for e in range(B)]
+    cams = [synth.make_camera(W, H, "side", jitter_seed=e) for e in range(B)]
+    st = lambda key: torch.tensor(np.stack([getattr(g, key) for g in gs])).cuda()
+    r = BatchedRasterizer("cuda")
+    color, radii, depth = r.forward(
+        st("means3D"), st("opacities"), viewmatrix=torch.tensor(np.stack([c.view for c in cams])).cuda(),
+        projmatrix=torch.tensor(np.stack([c.proj for c in cams])).cuda(),
+        campos=torch.tensor(np.stack([c.campos for c in cams])).cuda(), bg=torch.zeros(3).cuda(), W=W, H=H,
+        tanfovx=cams[0].tanfovx, tanfovy=cams[0].tanfovy, shs=st("shs"), scales=st("scales"), rotations=st("rotations"),
+        max_instances=8 * B * P)
+    total, overflow = r.status()
+    assert not overflow and total > 0
+    it = r.intermediates()
+    off = it["tile_offset"].cpu().numpy().astype(np.int64)
+    assert off[-1] == total == int(it["tiles_touched"].sum())
+    keys = it["keys"][:total].cpu().numpy()
+    brk = np.zeros(total, bool)
+    brk[off[1:-1][off[1:-1] < total]] = True
+    assert (np.diff(keys)[~brk[1:]] > 0).all(), "every tile list strictly ascending in (depth, id)"
+    assert torch.isfinite(color).all() and float(color.min()) >= 0.0
+    assert float(depth.min()) > 0.0 and float(depth.max()) <= 15.0
+    print(f"R/P = {total / (B * P):.3f}, mean list length = {total / (B * (W // 16) * (H // 16)):.1f}")

@@ -1,0 +1,479 @@
+#!/usr/bin/env python
+"""bench.py -- env.step()/sec (physics + render) for parallel PhysTwin environments.
+
+    python bench.py --gpus 1 --steps 5 --warmup 3              # this repository's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): rope PhysTwin (synthetic, N=2048 particles / S=32889
+springs), 256 parallel envs per GPU, 10 substeps per step, one 512x512 RGB-D render per env of
+200,000 Gaussians (10% bound to the particles).  A step is one pass of the hot path over all
+envs: per-frame collision-graph rebuild -> 10 substeps -> re-bind object Gaussians -> render.
+Multi-GPU: envs shard statically, one process per GPU, no data-path collective; one NCCL
+all-gather of {steps, seconds, checksum(x), checksum(rgb)} at the end (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over
+ranks); `e2e` is the same loop driven from HOST buffers: per step the gripper-motion tables and
+camera matrices are copied from pinned host memory, and particle states + rendered RGB-D are
+copied back to pinned host memory, all inside the timed region.
+
+`--impl reference` times the reference pipeline on the same box: the CPU restatement of
+sim/physics/spring_mass_warp.py (oracle/physics_ref.c -- the reference's Warp path cannot run:
+warp-lang is not installable offline) on all host cores, plus the UNMODIFIED reference CUDA
+rasterizer (oracle/_ref, built from /root/reference) called once per env with its own blocking
+num_rendered read-back, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "env_steps_per_sec"
+UNIT = "env.step/s"
+STAGES = ("preprocess", "scan", "emit", "tile_sort", "composite")
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="rope")
+    ap.add_argument("--envs", type=int, default=256, help="environments per GPU")
+    ap.add_argument("--res", type=int, nargs=2, default=[512, 512], metavar=("W", "H"))
+    ap.add_argument("--cameras", type=int, default=1)
+    ap.add_argument("--substeps", type=int, default=10)
+    ap.add_argument("--gaussians", type=int, default=200_000)
+    ap.add_argument("--ref-envs", type=int, default=0, help="reference arm: envs per step (0 = host cores, <= 64)")
+    ap.add_argument("--cpu-sample-envs", type=int, default=0, help="cpu_baseline sample size (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args):
+    from real2sim_eval_b200 import _lib
+    from real2sim_eval_b200.envs import BatchedEnv, EnvBatchConfig
+
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    W, H = args.res
+    cfg = EnvBatchConfig(scene=args.scene, E=args.envs, W=W, H=H, cameras=args.cameras, n_substeps=args.substeps,
+                         P=args.gaussians, env_offset=rank * args.envs)
+    env = BatchedEnv(cfg, dev)
+    lib = _lib.load()
+    E, ns = cfg.E, cfg.n_substeps
+    n_frames = args.warmup + args.steps + (0 if args.no_e2e else args.warmup + args.steps) + 2
+    acts = [env.make_actions(f) for f in range(n_frames)]           # host numpy, made before any timing
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    acts_pinned = [tuple(pin(a) for a in act) for act in acts]
+    dev_bufs = tuple(torch.empty_like(t, device=dev) for t in acts_pinned[0])
+
+    def upload(i):
+        for d, h in zip(dev_bufs, acts_pinned[i]):
+            d.copy_(h, non_blocking=True)
+        return dev_bufs
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident loop: motion tables already on the device
+    motions_dev = [tuple(t.to(dev) for t in act) for act in acts_pinned[:args.warmup + args.steps]]
+    for i in range(args.warmup):
+        env.step(motions_dev[i])
+    total, overflow = env.raster.status()
+    if overflow:
+        raise RuntimeError(f"instance capacity exceeded ({total} > {env.max_instances})")
+    lib.r2s_raster_set_profile(1)
+    stage_ms = np.zeros(len(STAGES))
+    phys_ms = 0.0
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pe0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pe1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    import ctypes
+    prof = (ctypes.c_float * 5)()
+    ev0.record()
+    for k in range(args.steps):
+        m = motions_dev[args.warmup + k]
+        # (same body as env.step, with events around the physics launch for the per-kernel report)
+        if env.phys.self_collision:
+            env.phys.update_collision_graph()
+        env.phys.set_mesh_motion(*m)
+        pe0[k].record()
+        env.phys.step()
+        pe1[k].record()
+        env._skin()
+        env.raster.forward(env.means3D, env.opacities, viewmatrix=env.view, projmatrix=env.proj, campos=env.campos,
+                           bg=env.bg, W=W, H=H, tanfovx=env.cams[0].tanfovx, tanfovy=env.cams[0].tanfovy, shs=env.shs,
+                           scales=env.scales, rotations=env.rotations, sh_degree=0, z_threshold=0.05,
+                           views_per_scene=cfg.cameras, max_instances=env.max_instances, out_color=env.color,
+                           out_depth=env.depth, want_radii=False)
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    _lib.check(lib.r2s_raster_get_profile(prof), "get_profile")   # stages of the LAST timed step
+    stage_ms = np.array(list(prof), dtype=np.float64)
+    phys_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe0, pe1)]))
+    lib.r2s_raster_set_profile(0)
+    total, overflow = env.raster.status()
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_max = float(t.item())
+    else:
+        ms_max = ms_total
+    value = world * E * args.steps / (ms_max / 1e3)
+
+    # ---- end-to-end loop: host buffers in, host buffers out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        x_host = torch.empty((E, env.base.N, 3), dtype=torch.float32).pin_memory()
+        v_host = torch.empty_like(x_host).pin_memory()
+        color_host = torch.empty(env.color.shape, dtype=torch.float32).pin_memory()
+        depth_host = torch.empty(env.depth.shape, dtype=torch.float32).pin_memory()
+        h2d = sum(t.numel() * 4 for t in acts_pinned[0]) + (env.view_h.numel() + env.proj_h.numel() + env.campos_h.numel()) * 4
+        d2h = (x_host.numel() + v_host.numel() + color_host.numel() + depth_host.numel()) * 4
+
+        def e2e_step(i):
+            m = upload(i)
+            env.view.copy_(env.view_h, non_blocking=True)
+            env.proj.copy_(env.proj_h, non_blocking=True)
+            env.campos.copy_(env.campos_h, non_blocking=True)
+            env.step(m)
+            xs, vs = env.phys.get_state()
+            x_host.copy_(xs, non_blocking=True)
+            v_host.copy_(vs, non_blocking=True)
+            color_host.copy_(env.color, non_blocking=True)
+            depth_host.copy_(env.depth, non_blocking=True)
+
+        base_i = args.warmup + args.steps
+        for i in range(args.warmup):
+            e2e_step(base_i + i)
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            e2e_step(base_i + args.warmup + i)
+        e1.record()
+        barrier()
+        ms_e2e = e0.elapsed_time(e1)
+        if world > 1:
+            import torch.distributed as dist
+            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t.item())
+        e2e = {"value": world * E * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
+               "checksum_rgb_host": float(color_host.double().sum())}
+
+    # ---- metrics all-gather (the only collective)
+    cx = float(env.phys.x.double().sum())
+    crgb = float(env.color.double().sum())
+    gathered = [[args.steps, ms_total / 1e3, cx, crgb]]
+    if world > 1:
+        import torch.distributed as dist
+        mine = torch.tensor(gathered[0], device=dev, dtype=torch.float64)
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine)
+        gathered = [o.tolist() for o in out]
+
+    # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md §8d)
+    pk, pk_kind = peaks()
+    B, P, T = env.B, cfg.P, (W // 16) * (H // 16)
+    R = total
+    alg = {
+        "phys_frame": E * ns * (52 * env.base.N + 16 * env.base.S),
+        "preprocess": B * P * (44 + 12 * 1) + B * P * 40,
+        "emit": R * 12,
+        "tile_sort": R * 24,
+        "composite": R * 40 + B * W * H * 16,
+    }
+    times = {"phys_frame": phys_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
+             "tile_sort": stage_ms[3], "composite": stage_ms[4]}
+    dom = max(times, key=times.get)
+    ach = alg[dom] / (times[dom] / 1e3) / 1e9
+    kernels = {k: {"ms": round(float(v), 4), "alg_gbs": round(alg[k] / (v / 1e3) / 1e9, 1) if k in alg and v > 0 else None}
+               for k, v in times.items()}
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": round(ach, 1), "peak": pk["hbm_gbs"], "peak_source": pk_kind,
+                "unit": "GB/s", "frac": round(ach / pk["hbm_gbs"], 4), "traffic": traffic,
+                "algorithmic_bytes_per_launch": int(alg[dom]), "kernels": kernels}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "impl": "ours",
+        "config": {"workload": f"{cfg.scene} PhysTwin x {E} envs/GPU, {ns} substeps/step, {cfg.cameras} x {W}x{H} "
+                               f"render of {P} Gaussians per env (BASELINE configs[1])",
+                   "envs_per_gpu": E, "global_envs": world * E, "particles": env.base.N, "springs": env.base.S,
+                   "substeps": ns, "resolution": [W, H], "cameras": cfg.cameras, "gaussians_per_env": P,
+                   "instances_per_step": int(R), "instances_per_gaussian": round(R / (B * P), 3),
+                   "mean_tile_list": round(R / (B * T), 1), "parallelism": f"env-shard x{world}",
+                   "l2_policy": "inputs larger than L2 (2.9 GB of Gaussians + 1.07 GB of images per step)"},
+        "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+        "metrics_allgather": {"per_rank": gathered, "fields": ["steps", "seconds", "checksum_x", "checksum_rgb"]},
+    }
+    if rank == 0 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, env)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return line if rank == 0 else None
+
+
+# ----------------------------------------------------------------------------- CPU baseline (oracle port)
+def _oracle_envs(scene, n, n_substeps, seed, offset=0, mesh=None):
+    import r2s_testutil as util
+    from real2sim_eval_b200 import synth
+    envs = []
+    for e in range(n):
+        s = synth.pose_scene(scene, seed + offset + e)
+        envs.append(util.oracle_from_scene(s, n_substeps, mesh=mesh))
+    return envs
+
+
+def cpu_baseline(args, env=None):
+    """oracle/ on the host cores: physics (all cores, one env per thread) + CPU rasterizer oracle
+    on a bounded sample of the same workload."""
+    import r2s_testutil as util
+    from oracle import physics_ref, raster_ref
+    from real2sim_eval_b200 import synth
+    from concurrent.futures import ThreadPoolExecutor
+
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample_envs or min(cores, 32)
+    W, H = args.res
+    scene = {"rope": synth.make_rope, "sloth": synth.make_sloth, "tblock": synth.load_tblock}[args.scene]()
+    g = synth.make_gripper(center=(float(scene.x[:, 0].mean()), float(scene.x[:, 1].mean()), 0.004), gap=0.03)
+    mesh = util.gripper_mesh_dict(g)
+    envs = _oracle_envs(scene, n, args.substeps, 1234, mesh=mesh)
+    gss = [synth.make_gaussians(1234 + e, args.gaussians, scene.x, n_object=0) for e in range(min(n, 4))]
+    cams = [synth.make_camera(W, H, "side", jitter_seed=e) for e in range(n)]
+
+    def render(e):
+        gs = gss[e % len(gss)]
+        c = cams[e]
+        raster_ref.rasterize(gs.means3D, gs.opacities, viewmatrix=c.view, projmatrix=c.proj, campos=c.campos,
+                             bg=np.zeros(3, np.float32), W=W, H=H, tanfovx=c.tanfovx, tanfovy=c.tanfovy, shs=gs.shs,
+                             scales=gs.scales, rotations=gs.rotations, z_threshold=0.05)
+
+    t0 = time.perf_counter()
+    for o in envs:
+        o.update_collision_graph()
+    physics_ref.step_batch(envs)                       # OpenMP: one env per thread
+    t_phys = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    with ThreadPoolExecutor(max_workers=min(cores, n)) as ex:   # ctypes releases the GIL
+        list(ex.map(render, range(n)))
+    t_rend = time.perf_counter() - t1
+    dt = t_phys + t_rend
+    return {"value": n / dt, "unit": UNIT, "cores": min(cores, n), "kind": "port",
+            "sample": f"{n} envs x 1 step ({args.substeps} substeps + one {W}x{H} render of {args.gaussians} Gaussians) "
+                      f"with oracle/physics_ref.c + oracle/raster_ref.c, one env per host thread",
+            "physics_s": round(t_phys, 4), "render_s": round(t_rend, 4),
+            "physics_env_substeps_per_s": n * args.substeps / t_phys}
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    """CPU physics (oracle port of the Warp path, all host threads) + the unmodified reference CUDA
+    rasterizer called once per env, as the reference's env loop would (one render + one blocking
+    read-back per call).  Bounded sample: ref_envs environments per step."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return None
+    import r2s_testutil as util
+    import ref_raster
+    from oracle import physics_ref
+    from real2sim_eval_b200 import synth
+
+    if not ref_raster.available():
+        return {"impl": "reference", "unavailable": "oracle/_ref/libref_raster.so missing (build needs /root/reference)"}
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cores = os.cpu_count() or 1
+    n = args.ref_envs or min(cores, 64)
+    W, H = args.res
+    P = args.gaussians
+    scene = {"rope": synth.make_rope, "sloth": synth.make_sloth, "tblock": synth.load_tblock}[args.scene]()
+    g = synth.make_gripper(center=(float(scene.x[:, 0].mean()), float(scene.x[:, 1].mean()), 0.004), gap=0.03)
+    envs = _oracle_envs(scene, n, args.substeps, 1234, mesh=util.gripper_mesh_dict(g))
+    tables = synth.gripper_motion(g, args.substeps, 5e-5, eef_vel=(0.02, 0.0, -0.01))
+    for o in envs:
+        o.set_mesh_interactive(*tables)
+    # Gaussians / cameras: same generator as our arm's BatchedEnv (device RNG), one set per env
+    gen = torch.Generator(device=dev)
+    scenes_t, cams = [], []
+    lo, hi = torch.tensor([-0.1, -0.6, 0.0], device=dev), torch.tensor([1.1, 0.6, 0.6], device=dev)
+    for e in range(n):
+        gen.manual_seed(1234 + 7 * e + 1)
+        means = lo + (hi - lo) * torch.rand((P, 3), device=dev, generator=gen)
+        scales = torch.exp(np.log(0.006) + 0.5 * torch.randn((P, 3), device=dev, generator=gen))
+        q = torch.randn((P, 4), device=dev, generator=gen)
+        rots = q / q.norm(dim=1, keepdim=True)
+        opac = torch.sigmoid(1.5 + 1.5 * torch.randn((P, 1), device=dev, generator=gen))
+        shs = (torch.rand((P, 1, 3), device=dev, generator=gen) - 0.5) / 0.28209479177387814
+        scenes_t.append(dict(means3D=means.contiguous(), scales=scales.contiguous(), rotations=rots.contiguous(),
+                             opacities=opac.contiguous(), shs=shs.contiguous()))
+        c = synth.make_camera(W, H, "side", jitter_seed=1234 + 13 * e)
+        cams.append((c, torch.tensor(c.view, device=dev), torch.tensor(c.proj, device=dev),
+                     torch.tensor(c.campos, device=dev)))
+    bg = torch.zeros(3, device=dev)
+    color = torch.empty((3, H, W), device=dev)
+    depth = torch.empty((1, H, W), device=dev)
+    radii = torch.empty(P, dtype=torch.int32, device=dev)
+
+    def step():
+        for o in envs:
+            o.update_collision_graph()
+        physics_ref.step_batch(envs)
+        rendered = 0
+        for e in range(n):
+            c, v, pr, cp = cams[e]
+            rendered += ref_raster.forward_torch(scenes_t[e], v, pr, cp, bg, W, H, c.tanfovx, c.tanfovy, 0, 0.05,
+                                                 color, depth, radii)
+        torch.cuda.synchronize(dev)
+        return rendered
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    sampler.start()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rendered = step()
+    dt = time.perf_counter() - t0
+    clocks = sampler.stop()
+    value = n * args.steps / dt
+    # split for the record (one more untimed step)
+    t1 = time.perf_counter()
+    for o in envs:
+        o.update_collision_graph()
+    physics_ref.step_batch(envs)
+    t_phys = time.perf_counter() - t1
+    return {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "impl": "reference",
+        "config": {"workload": f"{args.scene} PhysTwin, bounded sample of {n} envs per step (of {args.envs}), "
+                               f"{args.substeps} substeps/step, one {W}x{H} render of {P} Gaussians per env",
+                   "envs_per_step": n, "substeps": args.substeps, "resolution": [W, H], "gaussians_per_env": P,
+                   "instances_last_step": int(rendered)},
+        "clocks": clocks, "gpu_launches": 0,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port+reference",
+                         "sample": f"{n} envs per step: physics = oracle/physics_ref.c (CPU restatement of the Warp "
+                                   f"kernels; warp-lang not installable) on {cores} host threads, render = unmodified "
+                                   f"reference CUDA rasterizer (oracle/_ref) once per env with its blocking read-back",
+                         "physics_s_per_step": round(t_phys, 4)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        line = run_reference(args)
+    else:
+        line = run_ours(args)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -41,6 +41,9 @@ typedef struct r2s_phys_desc {
     int32_t coll_row_cap;   /* candidate-list row capacity; 0 -> 64.
                                [reference: 500 with no bound check, SMW:226,544-549]  */
     int32_t threads;        /* CTA size of the frame kernel; 0 -> default            */
+    int32_t precise;        /* 1: IEEE sqrt/divide in the reference's expression order (SMW:87-99);
+                               0 (default): 1/len by rsqrt + one Newton step and 1/rest precomputed --
+                               the same formula to a few ulp, ~2x faster          */
     float dt, dashpot_damping, drag_damping;
     float spring_Y_min, spring_Y_max, collision_dist;
     float collide_elas, collide_fric;           /* SMW:591-598 */

@@ -53,13 +53,13 @@ __device__ __forceinline__ float3 xyz(float4 a) { return f3(a.x, a.y, a.z); }
 
 // ------------------------------------------------------------------ kernel params
 struct FrameParams {
-    int E, N, n_sub, has_self_collision, use_pusher, sign_mode;
+    int E, N, n_sub, has_self_collision, use_pusher, sign_mode, precise;
     int V, F, n_dyn, coll_cap, stage_dyn, smem_forces;
     float dt, dashpot, drag_damping, rf, coll_dist;
     float c_elas, c_fric, ce_elas, ce_fric, cs_elas, cs_fric;
     const int* row_ptr;     // [N+1]
     const int2* nbr_k;      // [nd] {neighbour, float bits of clamped stiffness (<0: inactive)}
-    const float* rest;      // [E or 1][nd]
+    const float* rest;      // [E or 1][nd]: rest length (precise) or its reciprocal (fast)
     long long rest_stride;  // nd or 0
     const float* mass;      // [N]
     const int* mask;        // [N]
@@ -139,16 +139,20 @@ __device__ __forceinline__ float solid_angle(float3 a, float3 b, float3 c, float
     return 2.0f * atan2f(det, den);
 }
 
-// wp.mesh_query_point_sign_winding_number restated brute force (SMW:322-324):
-// strictly smaller squared distance from max_dist^2, faces in ascending index,
-// sign from the exact winding number against `threshold`.
-__device__ bool mesh_query(const MeshView& m, float3 p, float max_dist, float threshold,
-                           int sign_mode, int& face, float& u, float& v, float& sign)
+// wp.mesh_query_point_sign_winding_number restated brute force (SMW:322-324), evaluated by
+// one WARP per query point: lanes stride the faces, then an arg-min / sum reduction.
+// Semantics are those of a sequential scan: strictly smaller squared distance from
+// max_dist^2 wins and ties go to the lower face index; sign from the exact winding number
+// against `threshold`.  All lanes return the same result.
+__device__ __noinline__ bool mesh_query_warp(const MeshView& m, float3 p, float max_dist, float threshold,
+                                             int sign_mode, int& face, float& u, float& v, float& sign)
 {
+    const unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
     float best = max_dist * max_dist;
-    int hit = -1;
+    int hit = 0x7fffffff;
     float bu = 0.f, bv = 0.f;
-    for (int fc = 0; fc < m.F; ++fc) {
+    for (int fc = lane; fc < m.F; fc += 32) {
         const int* t = m.faces + 3 * fc;
         float3 a = m.vert(t[0]), b = m.vert(t[1]), c = m.vert(t[2]);
         float uu, vv;
@@ -158,14 +162,25 @@ __device__ bool mesh_query(const MeshView& m, float3 p, float max_dist, float th
         float d2 = dot3(d, d);
         if (d2 < best) { best = d2; hit = fc; bu = uu; bv = vv; }
     }
-    if (hit < 0) return false;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(kFull, best, o);
+        const int oh = __shfl_xor_sync(kFull, hit, o);
+        const float ou = __shfl_xor_sync(kFull, bu, o);
+        const float ov = __shfl_xor_sync(kFull, bv, o);
+        // lanes that found nothing keep hit = INT_MAX and best = max_dist^2, so they never win a tie
+        if (ob < best || (ob == best && oh < hit)) { best = ob; hit = oh; bu = ou; bv = ov; }
+    }
+    if (hit == 0x7fffffff) return false;
     face = hit; u = bu; v = bv;
     if (sign_mode == 1) { sign = 1.0f; return true; }
     float total = 0.0f;
-    for (int fc = 0; fc < m.F; ++fc) {
+    for (int fc = lane; fc < m.F; fc += 32) {
         const int* t = m.faces + 3 * fc;
         total += solid_angle(m.vert(t[0]), m.vert(t[1]), m.vert(t[2]), p);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
     float wn = total * 0.25f * 0.31830988618379067f;
     sign = (wn > threshold) ? -1.0f : 1.0f;
     return true;
@@ -179,30 +194,30 @@ __device__ __forceinline__ float3 mesh_eval(const MeshView& m, int face, float u
 
 // ------------------------------------------------------------------ frame kernel
 // G = lanes cooperating on one particle's adjacency row in phase A.
-template <int G, bool kSmemState>
+// kPrecise: IEEE sqrt / divisions in the reference's expression order (SMW:87-99).
+// !kPrecise: one rsqrt + Newton step gives 1/len, the rest length is stored as its reciprocal;
+// same formula, ~4x fewer instructions per spring, results within a few ulp of the precise path.
+template <int G, bool kSmemState, bool kPrecise>
 __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ float4 smem4[];
     const int e = blockIdx.x;
     const int tid = threadIdx.x;
     const int nthreads = blockDim.x;
     const int N = p.N;
 
-    // ---- carve shared memory
-    unsigned char* sp = smem_raw;
-    float4* sx;
-    float4* sv;
-    float* svb;  // [3][N]
-    if (kSmemState) {
-        sx = reinterpret_cast<float4*>(sp); sp += sizeof(float4) * N;
-        sv = reinterpret_cast<float4*>(sp); sp += sizeof(float4) * N;
-        svb = reinterpret_cast<float*>(sp); sp += sizeof(float) * 3 * ((N + 3) & ~3);
-    } else {
-        sx = p.x4 + (size_t)e * N;
-        sv = p.v4 + (size_t)e * N;
-        svb = p.vb_scratch + (size_t)e * 3 * N;
-    }
+    // ---- carve shared memory (pointers derived directly from the shared array so that the
+    //      compiler emits LDS/STS rather than generic loads)
+    const int Npad = (N + 3) & ~3;
+    float4* const sx = kSmemState ? smem4 : p.x4 + (size_t)e * N;
+    float4* const sv = kSmemState ? smem4 + N : p.v4 + (size_t)e * N;
+    float* const svb = kSmemState ? reinterpret_cast<float*>(smem4 + 2 * N) : p.vb_scratch + (size_t)e * 3 * N;  // [3][N]
+    unsigned char* sp = reinterpret_cast<unsigned char*>(smem4) +
+                        (kSmemState ? sizeof(float4) * 2 * N + sizeof(float) * 3 * Npad : 0);
     float* s_aabb = reinterpret_cast<float*>(sp); sp += sizeof(float) * 16;  // [0..5] dyn, [6..11] static
+    int* s_ncand = reinterpret_cast<int*>(s_aabb + 12);                      // candidates of this substep
+    int* s_cand = reinterpret_cast<int*>(sp);                                // particles near the mesh
+    if (p.F > 0) sp += sizeof(int) * ((N + 3) & ~3);
     float* s_dyn = reinterpret_cast<float*>(sp);
     if (p.stage_dyn) sp += sizeof(float) * 3 * ((p.n_dyn + 3) & ~3);
     float* s_forces = reinterpret_cast<float*>(sp);
@@ -267,8 +282,10 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         lo[c] = fminf(lo[c], __shfl_xor_sync(kFull, lo[c], o));
                         hi[c] = fmaxf(hi[c], __shfl_xor_sync(kFull, hi[c], o));
                     }
-                if (tid == 0)
+                if (tid == 0) {
                     for (int c = 0; c < 3; ++c) { s_aabb[c] = lo[c]; s_aabb[3 + c] = hi[c]; }
+                    *s_ncand = 0;
+                }
             } else if (tid < 64) {  // SMW:900 collision_forces.zero_()
                 for (int k = tid - 32; k < 3 * p.F; k += 32) forces[k] = 0.0f;
             }
@@ -286,12 +303,25 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                 if (kk >= 0.0f) {  // exp(Y) > Y_min guard (SMW:75), resolved at set_spring_Y time
                     const float3 xj = xyz(sx[nk.x]), vj = xyz(sv[nk.x]);
                     const float3 dis = xj - xi;
-                    const float dis_len = len3(dis);
-                    const float3 d = dis / fmaxf(dis_len, 1e-6f);
-                    const float3 spring_force = d * (kk * (dis_len / r - 1.0f));
-                    const float v_rel = dot3(vj - vi, d);
-                    const float3 dashpot = d * (p.dashpot * v_rel);
-                    acc = acc + (spring_force + dashpot);
+                    if (kPrecise) {
+                        const float dis_len = len3(dis);
+                        const float3 d = dis / fmaxf(dis_len, 1e-6f);
+                        const float3 spring_force = d * (kk * (dis_len / r - 1.0f));
+                        const float v_rel = dot3(vj - vi, d);
+                        const float3 dashpot = d * (p.dashpot * v_rel);
+                        acc = acc + (spring_force + dashpot);
+                    } else {
+                        const float len2 = dot3(dis, dis);
+                        const float c2 = fmaxf(len2, 1e-12f);         // max(len, 1e-6)^2
+                        float y = rsqrtf(c2);
+                        y = y * (1.5f - 0.5f * c2 * y * y);           // Newton step: 1/max(len,1e-6) to ~1 ulp
+                        const float dis_len = len2 >= 1e-12f ? len2 * y : sqrtf(len2);
+                        const float3 d = dis * y;
+                        const float3 spring_force = d * (kk * fmaf(dis_len, r, -1.0f));  // r = 1/rest
+                        const float v_rel = dot3(vj - vi, d);
+                        const float3 dashpot = d * (p.dashpot * v_rel);
+                        acc = acc + (spring_force + dashpot);
+                    }
                 }
             }
 #pragma unroll
@@ -376,17 +406,62 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
             dv0 = f3(g_dynvel[0], g_dynvel[1], g_dynvel[2]);
             dv1 = f3(g_dynvel[3], g_dynvel[4], g_dynvel[5]);
         }
+        // ground bounce + position update of one particle (SMW:424-474)
+        auto integrate_ground = [&](int i, float3 x0, float3 v0) {
+            const float x_z = x0.z, v_z = v0.z;
+            const float next_x_z = (x_z + v_z * dt) * rf;
+            float3 v1; float toi;
+            if (next_x_z < 0.0f && v_z * rf < -1e-4f) {
+                const float3 normal = f3(0.0f, 0.0f, 1.0f) * rf;
+                const float3 v_normal = normal * dot3(v0, normal);
+                const float3 v_tao = v0 - v_normal;
+                const float v_normal_len = len3(v_normal);
+                const float v_tao_len = fmaxf(len3(v_tao), 1e-6f);
+                const float ce = clampf(p.c_elas, 0.0f, 1.0f);
+                const float cf = clampf(p.c_fric, 0.0f, 2.0f);
+                const float3 v_normal_new = v_normal * (-ce);
+                const float a = fmaxf(0.0f, 1.0f - cf * (1.0f + ce) * v_normal_len / v_tao_len);
+                v1 = v_normal_new + v_tao * a;
+                toi = -(x_z - 0.0f) / v_z;
+            } else {
+                v1 = v0; toi = 0.0f;
+            }
+            const float3 xn = x0 + v0 * toi + v1 * (dt - toi);
+            sx[i] = make_float4(xn.x, xn.y, xn.z, 0.0f);
+            sv[i] = make_float4(v1.x, v1.y, v1.z, 0.0f);
+        };
+        // C1: one thread per particle.  Particles whose advanced position lies outside the mesh
+        // bounding box (grown by max_dist) cannot hit: they finish here.  The rest are queued.
         for (int i = tid; i < N; i += nthreads) {
-            float3 x0 = xyz(sx[i]);
-            float3 v0 = run_B ? xyz(sv[i]) : f3(svb[i], svb[N + i], svb[2 * N + i]);
+            const float3 x0 = xyz(sx[i]);
+            const float3 v0 = run_B ? xyz(sv[i]) : f3(svb[i], svb[N + i], svb[2 * N + i]);
             if (has_mesh) {
+                const float3 next_x = x0 + v0 * dt;
+                const bool near_box = next_x.x >= box_lo.x && next_x.x <= box_hi.x && next_x.y >= box_lo.y &&
+                                      next_x.y <= box_hi.y && next_x.z >= box_lo.z && next_x.z <= box_hi.z;
+                if (near_box) {
+                    s_cand[atomicAdd(s_ncand, 1)] = i;
+                    if (!run_B) sv[i] = make_float4(v0.x, v0.y, v0.z, 0.0f);  // C2 reads v_before_ground from sv
+                    continue;
+                }
+                integrate_ground(i, next_x, v0);  // mesh_collision with no hit still advances x (SMW:417-421)
+            } else {
+                integrate_ground(i, x0, v0);
+            }
+        }
+        // C2: one warp per queued particle (mesh_collision, SMW:295-421, then the ground step)
+        if (has_mesh) {
+            __syncthreads();
+            const int n_cand = *s_ncand;
+            const int lane = tid & 31;
+            for (int c = tid >> 5; c < n_cand; c += nthreads >> 5) {
+                const int i = s_cand[c];
+                const float3 x0 = xyz(sx[i]);
+                float3 v0 = xyz(sv[i]);
                 float3 next_x = x0 + v0 * dt;
                 float3 next_v = v0;
                 int face; float u, v, sign;
-                // the box test only skips queries that cannot hit (every triangle farther than max_dist)
-                const bool near_box = next_x.x >= box_lo.x && next_x.x <= box_hi.x && next_x.y >= box_lo.y &&
-                                      next_x.y <= box_hi.y && next_x.z >= box_lo.z && next_x.z <= box_hi.z;
-                if (near_box && mesh_query(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face, u, v, sign)) {
+                if (mesh_query_warp(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face, u, v, sign)) {
                     int is_gripper;
                     const int mm = p.mesh_map[face];
                     if (!p.use_pusher) is_gripper = (mm == 0) ? 1 : ((mm == 1) ? 2 : 0);
@@ -396,7 +471,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                     const float dist = len3(delta) * sign;
                     const float margin = (is_gripper >= 1 && !p.use_pusher) ? 0.005f : 0.001f;
                     const float err = dist - margin;
-                    if (err < 0.0f) {
+                    if (err < 0.0f) {  // warp-uniform: every lane holds the same query result
                         const float3 normal = normalize3(delta) * sign;
                         float3 real_dyn = f3(0.f, 0.f, 0.f);
                         float ce, cf;
@@ -422,7 +497,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         if (is_gripper >= 1) {
                             next_x = x0 + next_v * dt;
                             int face2; float u2, v2, sign2;
-                            if (mesh_query(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face2, u2, v2, sign2)) {
+                            if (mesh_query_warp(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face2, u2, v2, sign2)) {
                                 const float3 p2 = mesh_eval(mesh, face2, u2, v2);
                                 const float3 delta2 = next_x - p2;
                                 const float err2 = len3(delta2) * sign2 - margin;
@@ -434,38 +509,17 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         } else {
                             next_x = next_x - normal * err;
                         }
-                        const float3 dvn = (v_normal_new - v_normal) / dt;
-                        const int fm = p.face_map[face];
-                        atomicAdd(forces + 3 * fm, dvn.x);
-                        atomicAdd(forces + 3 * fm + 1, dvn.y);
-                        atomicAdd(forces + 3 * fm + 2, dvn.z);
+                        if (lane == 0) {
+                            const float3 dvn = (v_normal_new - v_normal) / dt;
+                            const int fm = p.face_map[face];
+                            atomicAdd(forces + 3 * fm, dvn.x);
+                            atomicAdd(forces + 3 * fm + 1, dvn.y);
+                            atomicAdd(forces + 3 * fm + 2, dvn.z);
+                        }
                     }
                 }
-                x0 = next_x;
-                v0 = next_v;
+                if (lane == 0) integrate_ground(i, next_x, next_v);
             }
-            // integrate_ground_collision
-            const float x_z = x0.z, v_z = v0.z;
-            const float next_x_z = (x_z + v_z * dt) * rf;
-            float3 v1; float toi;
-            if (next_x_z < 0.0f && v_z * rf < -1e-4f) {
-                const float3 normal = f3(0.0f, 0.0f, 1.0f) * rf;
-                const float3 v_normal = normal * dot3(v0, normal);
-                const float3 v_tao = v0 - v_normal;
-                const float v_normal_len = len3(v_normal);
-                const float v_tao_len = fmaxf(len3(v_tao), 1e-6f);
-                const float ce = clampf(p.c_elas, 0.0f, 1.0f);
-                const float cf = clampf(p.c_fric, 0.0f, 2.0f);
-                const float3 v_normal_new = v_normal * (-ce);
-                const float a = fmaxf(0.0f, 1.0f - cf * (1.0f + ce) * v_normal_len / v_tao_len);
-                v1 = v_normal_new + v_tao * a;
-                toi = -(x_z - 0.0f) / v_z;
-            } else {
-                v1 = v0; toi = 0.0f;
-            }
-            const float3 xn = x0 + v0 * toi + v1 * (dt - toi);
-            sx[i] = make_float4(xn.x, xn.y, xn.z, 0.0f);
-            sv[i] = make_float4(v1.x, v1.y, v1.z, 0.0f);
         }
         __syncthreads();
     }
@@ -639,12 +693,14 @@ __global__ void iota_kernel(int* p, int n)
 }
 
 __global__ void rest_gather_kernel(const float* __restrict__ rest, long long rest_stride_env,
-                                   const int* __restrict__ sid, float* __restrict__ out, int n_env, int nd)
+                                   const int* __restrict__ sid, float* __restrict__ out, int n_env, int nd,
+                                   int reciprocal)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)n_env * nd) return;
     const int e = (int)(idx / nd), k = (int)(idx % nd);
-    out[idx] = rest[(size_t)e * rest_stride_env + sid[k]];
+    const float r = rest[(size_t)e * rest_stride_env + sid[k]];
+    out[idx] = reciprocal ? 1.0f / r : r;
 }
 
 }  // namespace
@@ -715,6 +771,7 @@ int configure_launch(r2s_phys* h)
     if (h->F > 0) {
         size_t dynb = sizeof(float) * 3 * ((h->n_dyn + 3) & ~3);
         size_t fb = sizeof(float) * 3 * h->F;
+        misc += sizeof(int) * ((N + 3) & ~3);  // queue of particles near the mesh
         if (dynb <= 24 * 1024) { h->stage_dyn = 1; misc += dynb; }
         if (fb <= 24 * 1024) { h->smem_forces = 1; misc += fb; }
     }
@@ -726,20 +783,21 @@ int configure_launch(r2s_phys* h)
     return R2S_OK;
 }
 
+template <int G, bool kSmem, bool kPrecise>
+int launch_frame_t(r2s_phys* h, const FrameParams& fp, cudaStream_t st)
+{
+    R2S_CUDA_TRY(cudaFuncSetAttribute(frame_kernel<G, kSmem, kPrecise>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)h->smem_bytes));
+    frame_kernel<G, kSmem, kPrecise><<<h->d.E, h->threads, h->smem_bytes, st>>>(fp);
+    R2S_LAUNCH_CHECK();
+    return R2S_OK;
+}
+
 template <int G>
 int launch_frame(r2s_phys* h, const FrameParams& fp, cudaStream_t st)
 {
-    if (h->smem_state) {
-        R2S_CUDA_TRY(cudaFuncSetAttribute(frame_kernel<G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)h->smem_bytes));
-        frame_kernel<G, true><<<h->d.E, h->threads, h->smem_bytes, st>>>(fp);
-    } else {
-        R2S_CUDA_TRY(cudaFuncSetAttribute(frame_kernel<G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)h->smem_bytes));
-        frame_kernel<G, false><<<h->d.E, h->threads, h->smem_bytes, st>>>(fp);
-    }
-    R2S_LAUNCH_CHECK();
-    return R2S_OK;
+    if (h->smem_state) return h->d.precise ? launch_frame_t<G, true, true>(h, fp, st) : launch_frame_t<G, true, false>(h, fp, st);
+    return h->d.precise ? launch_frame_t<G, false, true>(h, fp, st) : launch_frame_t<G, false, false>(h, fp, st);
 }
 
 }  // namespace
@@ -897,7 +955,8 @@ int r2s_phys_set_rest_lengths(r2s_phys* h, const float* rest, int per_env, void*
     }
     if (h->nd == 0) return R2S_OK;
     const long long n = (long long)n_env * h->nd;
-    rest_gather_kernel<<<r2s::ceil_div(n, 256), 256, 0, st>>>(rest, h->d.S, h->sid, h->rest_csr, n_env, h->nd);
+    rest_gather_kernel<<<r2s::ceil_div(n, 256), 256, 0, st>>>(rest, h->d.S, h->sid, h->rest_csr, n_env, h->nd,
+                                                                 h->d.precise ? 0 : 1);
     R2S_LAUNCH_CHECK();
     return R2S_OK;
 }
@@ -1026,6 +1085,7 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     FrameParams p{};
     p.E = h->d.E; p.N = h->d.N; p.n_sub = ns;
     p.has_self_collision = h->d.self_collision; p.use_pusher = h->d.use_pusher; p.sign_mode = h->d.sign_mode;
+    p.precise = h->d.precise;
     p.V = h->V; p.F = h->F; p.n_dyn = h->n_dyn; p.coll_cap = h->coll_cap;
     p.stage_dyn = h->stage_dyn; p.smem_forces = h->smem_forces;
     p.dt = h->d.dt; p.dashpot = h->d.dashpot_damping; p.drag_damping = h->d.drag_damping;

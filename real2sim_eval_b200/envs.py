@@ -1,0 +1,179 @@
+"""Batched env.step(): E independent environments advanced by one frame each --
+physics substeps (one persistent launch), object Gaussians re-bound to the
+particles, one render per (env, camera) -- without a host synchronisation.
+
+This is the per-frame sequence of the reference's BaseEnv.step + get_obs
+(sim/envs/env.py:86-94, 53-74: physics.step -> renderer.update_state -> render)
+restricted to the two hot paths this repository implements; the LBS step between
+them is the translation-only stand-in of r2s_skin_translate.
+All device work goes to torch's current stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib, synth
+from .physics import BatchedSpringMass
+from .rasterizer import BatchedRasterizer
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+@dataclass
+class EnvBatchConfig:
+    scene: str = "rope"          # rope | sloth | tblock
+    E: int = 256                 # environments on this device
+    W: int = 512
+    H: int = 512
+    cameras: int = 1             # views per environment
+    n_substeps: int = 10
+    P: int = 200_000             # Gaussians per environment
+    obj_frac: float = 0.1        # fraction bound to the particles
+    knn: int = 16
+    seed: int = 1234
+    env_offset: int = 0          # global index of this shard's first env (multi-GPU sharding)
+    gripper: bool = True
+    instances_per_gaussian: float = 8.0
+
+
+def _scene(name: str) -> synth.Scene:
+    if name == "rope":
+        return synth.make_rope()
+    if name == "sloth":
+        return synth.make_sloth()
+    if name == "tblock":
+        return synth.load_tblock()
+    raise ValueError(name)
+
+
+class BatchedEnv:
+    """E environments of one scene type on one device, synthetic data."""
+
+    def __init__(self, cfg: EnvBatchConfig, device="cuda"):
+        self.cfg = cfg
+        self.device = dev = torch.device(device)
+        self.lib = _lib.load()
+        E = cfg.E
+        base = _scene(cfg.scene)
+        self.base = base
+        poses = [synth.pose_scene(base, cfg.seed + cfg.env_offset + e) for e in range(E)]
+        rest = np.stack([p.rest for p in poses])
+        pr = dict(base.params)
+        self.phys = BatchedSpringMass(E, base.springs, rest, num_particles=base.N, n_substeps=cfg.n_substeps,
+                                      log_spring_Y=base.log_Y, masses=base.mass, device=dev, **pr)
+        self.x_init = torch.tensor(np.stack([p.x for p in poses]), device=dev)
+        self.phys.set_state(self.x_init, torch.tensor(np.stack([p.v for p in poses]), device=dev))
+        if self.phys.self_collision:
+            self.phys.create_resting_case()
+        self.dt = pr["dt"]
+        # gripper: two fingers straddling the object near its centre, per-env motion tables
+        self.gripper = None
+        if cfg.gripper:
+            ctr = base.x.mean(0)
+            self.gripper = synth.make_gripper(center=(float(ctr[0]), float(ctr[1]), 0.004), gap=0.03)
+            g = self.gripper
+            self.phys.set_mesh(g.verts, g.faces, g.mesh_map, g.face_map, len(g.verts))
+            self.finger_pose = np.zeros((E, 3), np.float32)  # accumulated eef translation per env
+        # Gaussians: per-env sets generated on the device from per-env seeds
+        P = cfg.P
+        n_obj = int(P * cfg.obj_frac)
+        self.n_obj, self.K = n_obj, min(cfg.knn, base.N)
+        gen = torch.Generator(device=dev)
+        means = torch.empty((E, P, 3), device=dev)
+        scales = torch.empty((E, P, 3), device=dev)
+        rots = torch.empty((E, P, 4), device=dev)
+        opac = torch.empty((E, P, 1), device=dev)
+        shs = torch.empty((E, P, 1, 3), device=dev)
+        lo = torch.tensor([-0.1, -0.6, 0.0], device=dev)
+        hi = torch.tensor([1.1, 0.6, 0.6], device=dev)
+        # object Gaussians share their binding (idx, weights, rest offsets) across envs: one PhysTwin, E poses
+        rng = np.random.default_rng(cfg.seed)
+        from scipy.spatial import cKDTree
+        src = base.x[rng.integers(0, base.N, n_obj)].astype(np.float64) + rng.normal(0, 0.002, (n_obj, 3))
+        dist, idx = cKDTree(base.x).query(src, k=self.K)
+        idx = idx.reshape(n_obj, self.K)
+        w = 1.0 / np.maximum(dist.reshape(n_obj, self.K), 1e-6)
+        w = (w / w.sum(1, keepdims=True)).astype(np.float32)
+        self.bind_idx = torch.tensor(idx.astype(np.int32), device=dev)
+        self.bind_w = torch.tensor(w, device=dev)
+        self.g0 = torch.tensor(src.astype(np.float32), device=dev)
+        self.x0 = torch.tensor(base.x, device=dev)
+        for e in range(E):
+            gen.manual_seed(cfg.seed + 7 * (cfg.env_offset + e) + 1)
+            means[e] = lo + (hi - lo) * torch.rand((P, 3), device=dev, generator=gen)
+            scales[e] = torch.exp(np.log(0.006) + 0.5 * torch.randn((P, 3), device=dev, generator=gen))
+            q = torch.randn((P, 4), device=dev, generator=gen)
+            rots[e] = q / q.norm(dim=1, keepdim=True)
+            opac[e] = torch.sigmoid(1.5 + 1.5 * torch.randn((P, 1), device=dev, generator=gen))
+            shs[e] = (torch.rand((P, 1, 3), device=dev, generator=gen) - 0.5) / 0.28209479177387814
+        self.means3D, self.scales, self.rotations, self.opacities, self.shs = means, scales, rots, opac, shs
+        # cameras: cfg.cameras fixed views per env (side, and a top-down second view), small per-env jitter
+        cams = []
+        for e in range(E):
+            for c in range(cfg.cameras):
+                cams.append(synth.make_camera(cfg.W, cfg.H, "side" if c == 0 else "top",
+                                              jitter_seed=cfg.seed + 13 * (cfg.env_offset + e) + c))
+        self.cams = cams
+        self.view_h = torch.tensor(np.stack([c.view for c in cams])).pin_memory()
+        self.proj_h = torch.tensor(np.stack([c.proj for c in cams])).pin_memory()
+        self.campos_h = torch.tensor(np.stack([c.campos for c in cams])).pin_memory()
+        self.view, self.proj, self.campos = self.view_h.to(dev), self.proj_h.to(dev), self.campos_h.to(dev)
+        self.bg = torch.zeros(3, device=dev)
+        self.raster = BatchedRasterizer(dev)
+        self.B = E * cfg.cameras
+        self.max_instances = int(cfg.instances_per_gaussian * self.B * P)
+        self.color = torch.empty((self.B, 3, cfg.H, cfg.W), device=dev)
+        self.depth = torch.empty((self.B, 1, cfg.H, cfg.W), device=dev)
+        self.frame = 0
+        self._skin()
+
+    # ---- per-frame host-side action -> gripper motion tables (numpy, pinned by the caller if needed)
+    def make_actions(self, frame: int):
+        """Seeded per-env eef velocities for this frame and the per-substep tables the physics takes
+        (what sim/physics/phystwin.py:374-460 computes per frame from the policy's action)."""
+        cfg, E, ns = self.cfg, self.cfg.E, self.cfg.n_substeps
+        rng = np.random.default_rng(cfg.seed + 1000 * frame + cfg.env_offset)
+        vel = rng.uniform(-0.1, 0.1, (E, 3)).astype(np.float32)
+        vel[:, 2] = rng.uniform(-0.05, 0.02, E)
+        g = self.gripper
+        t = (np.arange(1, ns + 1, dtype=np.float32) * np.float32(self.dt))[None, :, None, None]
+        base_pts = g.verts[None, None] + self.finger_pose[:, None, None, :]
+        pts = (base_pts + vel[:, None, None, :] * t).astype(np.float32)            # (E, ns, 48, 3)
+        ctr = (g.verts.mean(0)[None, None] + self.finger_pose[:, None, :] + vel[:, None, :] * t[:, :, 0]).astype(np.float32)
+        dyn_vel = np.repeat((vel * 0.5)[:, None, :], 2, axis=1).astype(np.float32)  # (E, 2, 3)
+        dyn_omega = np.zeros((E, 1, 3), np.float32)
+        self.finger_pose = self.finger_pose + vel * np.float32(self.dt * ns)
+        return pts, ctr, dyn_vel, dyn_omega
+
+    def _skin(self):
+        c, dev = self.cfg, self.device
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.r2s_skin_translate(
+                c.E, self.base.N, c.P, self.n_obj, self.K, _ptr(self.bind_idx), _ptr(self.bind_w), _ptr(self.phys.x4),
+                _ptr(self.x0), _ptr(self.g0), _ptr(self.means3D),
+                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "r2s_skin_translate")
+
+    def step(self, motion=None):
+        """One frame for every env: [gripper tables ->] collision graph -> substeps -> skin -> render.
+        `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None."""
+        if self.phys.self_collision:
+            self.phys.update_collision_graph()       # once per frame (phystwin.py:365-366)
+        if motion is not None:
+            self.phys.set_mesh_motion(*motion)
+        self.phys.step()
+        self._skin()
+        c = self.cfg
+        self.raster.forward(self.means3D, self.opacities, viewmatrix=self.view, projmatrix=self.proj,
+                            campos=self.campos, bg=self.bg, W=c.W, H=c.H, tanfovx=self.cams[0].tanfovx,
+                            tanfovy=self.cams[0].tanfovy, shs=self.shs, scales=self.scales, rotations=self.rotations,
+                            sh_degree=0, z_threshold=0.05, views_per_scene=c.cameras,
+                            max_instances=self.max_instances, out_color=self.color, out_depth=self.depth,
+                            want_radii=False)
+        self.frame += 1
+        return self.color, self.depth

@@ -80,7 +80,7 @@ class BatchedSpringMass:
                  spring_Y_max=1e5, collision_dist=0.005, self_collision=True, reverse_z=False,
                  collide_elas=0.5, collide_fric=0.3, collide_eef_elas=0.0, collide_eef_fric=1.0,
                  collide_self_elas=0.5, collide_self_fric=0.3, use_pusher=False, sign_mode=0, coll_row_cap=0,
-                 threads=0, device="cuda"):
+                 threads=0, precise=False, device="cuda"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.R2SError("BatchedSpringMass needs a CUDA device: there is no CPU path")
@@ -101,6 +101,7 @@ class BatchedSpringMass:
         d.E, d.N, d.S, d.n_substeps = self.E, self.N, self.S, self.n_substeps
         d.self_collision, d.reverse_z, d.use_pusher = int(bool(self_collision)), int(bool(reverse_z)), int(bool(use_pusher))
         d.sign_mode, d.coll_row_cap, d.threads = int(sign_mode), int(coll_row_cap), int(threads)
+        d.precise = int(bool(precise))
         d.dt, d.dashpot_damping, d.drag_damping = dt, dashpot_damping, drag_damping
         d.spring_Y_min, d.spring_Y_max, d.collision_dist = spring_Y_min, spring_Y_max, collision_dist
         d.collide_elas, d.collide_fric = collide_elas, collide_fric
@@ -269,7 +270,7 @@ class SpringMassSystemWarp:
                  num_object_points, init_spring_Y=None, collide_elas=None, collide_fric=None, collide_eef_elas=None,
                  collide_eef_fric=None, collide_self_elas=None, collide_self_fric=None, init_collision_mask=None,
                  init_velocities=None, dynamic_meshes=None, static_meshes=None, dynamic_points=None,
-                 use_pusher=False, sign_mode=0):
+                 use_pusher=False, sign_mode=0, precise=True):
         cfg = phystwin_cfg
         self.device = torch.device(str(device))
         self.dt, self.num_substeps = cfg.dt, int(cfg.num_substeps)
@@ -298,7 +299,7 @@ class SpringMassSystemWarp:
             collide_eef_fric=g(collide_eef_fric, "collide_eef_fric"),
             collide_self_elas=g(collide_self_elas, "collide_self_elas"),
             collide_self_fric=g(collide_self_fric, "collide_self_fric"),
-            use_pusher=use_pusher, sign_mode=sign_mode, device=self.device)
+            use_pusher=use_pusher, sign_mode=sign_mode, precise=precise, device=self.device)
         self.wp_state = _State(self.sys)
         v0 = None if init_velocities is None else init_velocities[:num_object_points]
         self.set_init_state(init_vertices, v0)

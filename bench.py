@@ -303,6 +303,7 @@ def run_ours(args):
                    "envs_per_gpu": E, "global_envs": world * E, "particles": env.base.N, "springs": env.base.S,
                    "substeps": ns, "resolution": [W, H], "cameras": cfg.cameras, "gaussians_per_env": P,
                    "instances_per_step": int(R), "instances_per_gaussian": round(R / (B * P), 3),
+                   "super_tile_instances_per_step": int(env.raster.intermediates()["super_offset"][-1].item()),
                    "mean_tile_list": round(R / (B * T), 1), "parallelism": f"env-shard x{world}",
                    "l2_policy": "inputs larger than L2 (2.9 GB of Gaussians + 1.07 GB of images per step)"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,

@@ -54,9 +54,10 @@ class RasterArgs(C.Structure):  # include/r2s_raster.h: r2s_raster_args
 
 
 class RasterLayout(C.Structure):  # r2s_raster_layout
-    _fields_ = [(n, c_sz) for n in ("status", "depths", "radii", "tiles_touched", "rec_a", "rec_b", "rec_c",
-                                    "tile_count", "tile_offset", "tile_fill", "keys", "keys_alt", "total")] + \
-               [("tiles_x", c_i32), ("tiles_y", c_i32)]
+    _fields_ = [(n, c_sz) for n in ("status", "depths", "radii", "tiles_touched", "rec_a", "rec_b", "rec_c", "rects",
+                                    "tile_count", "tile_offset", "tile_fill", "keys", "keys_alt", "sorted_rect",
+                                    "total")] + \
+               [("tiles_x", c_i32), ("tiles_y", c_i32), ("super_x", c_i32), ("super_y", c_i32)]
 
 
 # every symbol include/*.h declares: (name, restype, argtypes)

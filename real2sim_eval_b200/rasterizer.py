@@ -137,7 +137,7 @@ class BatchedRasterizer:
         """Typed torch views of the workspace arrays (parity tests, accounting)."""
         B, P, W, H, cap = self.shape
         L, ws = self.layout, self.ws
-        T = L.tiles_x * L.tiles_y
+        T = L.super_x * L.super_y   # lists are kept per super-tile (4x4 tiles)
 
         def view(off, nbytes, dtype):
             return ws[off:off + nbytes].view(dtype)
@@ -149,10 +149,13 @@ class BatchedRasterizer:
             rec_a=view(L.rec_a, 16 * B * P, torch.float32).view(B, P, 4),
             rec_b=view(L.rec_b, 16 * B * P, torch.float32).view(B, P, 4),
             rec_c=view(L.rec_c, 4 * B * P, torch.float32).view(B, P),
-            tile_count=view(L.tile_count, 4 * B * T, torch.int32).view(B, T),
-            tile_offset=view(L.tile_offset, 4 * (B * T + 1), torch.int32),
+            rects=view(L.rects, 4 * B * P, torch.int32).view(B, P),
+            super_count=view(L.tile_count, 4 * B * T, torch.int32).view(B, T),
+            super_offset=view(L.tile_offset, 4 * (B * T + 1), torch.int32),
             keys=view(L.keys, 8 * cap, torch.int64),
+            sorted_rect=view(L.sorted_rect, 4 * cap, torch.int32),
             tiles=(L.tiles_x, L.tiles_y),
+            supers=(L.super_x, L.super_y),
         )
 
 

@@ -63,13 +63,30 @@ def _close_images(a, b, what):
     return frac
 
 
-def _sorted_lists(r, P):
-    """(ranges [T,2], list of per-tile id arrays) from the CUDA workspace, view 0."""
+def _super_lists(r, view=0):
+    """(offsets [ST+1], keys uint64, rects uint32) of the sorted super-tile lists of one view."""
     it = r.intermediates()
-    off = it["tile_offset"].cpu().numpy().astype(np.int64)
-    T = it["tiles"][0] * it["tiles"][1]
+    ST = it["supers"][0] * it["supers"][1]
+    off = it["super_offset"].cpu().numpy().astype(np.int64)[view * ST: (view + 1) * ST + 1]
     keys = it["keys"].cpu().numpy().view(np.uint64)
-    return off[:T + 1], keys
+    rects = it["sorted_rect"].cpu().numpy().view(np.uint32)
+    return off, keys, rects, it
+
+
+def _tile_lists(r, view=0):
+    """Per-tile Gaussian id lists, rebuilt on the host the way composite_kernel walks them: the
+    order-preserving subsequence of the tile's super-tile list whose rectangle contains the tile."""
+    off, keys, rects, it = _super_lists(r, view)
+    gx, gy = it["tiles"]
+    sgx = it["supers"][0]
+    out = []
+    for ty in range(gy):
+        for tx in range(gx):
+            s = (ty // 4) * sgx + tx // 4
+            k, rc = keys[off[s]:off[s + 1]], rects[off[s]:off[s + 1]]
+            keep = (tx >= (rc & 255)) & (tx < ((rc >> 16) & 255)) & (ty >= ((rc >> 8) & 255)) & (ty < (rc >> 24))
+            out.append((k[keep] & np.uint64(0xffffffff)).astype(np.uint32))
+    return out
 
 
 @pytest.mark.parametrize("W,H,P,seed", [(64, 64, 1500, 1), (128, 96, 4000, 2), (200, 120, 2500, 3)])
@@ -96,16 +113,17 @@ def test_matches_oracle_stagewise(W, H, P, seed):
     float_exact = np.array_equal(depths, aux["depths"]) and np.array_equal(radii, orad) and \
         np.array_equal(tt, aux["tiles_touched"].astype(np.int64)) and \
         np.array_equal(ra[vis, :2], aux["means2D"][vis])
-    off, keys = _sorted_lists(r, P)
-    assert total == off[-1]
-    for t in range(len(off) - 1):      # every tile list is sorted by (depth bits, id)
+    off, keys, rects, _ = _super_lists(r)
+    assert total == int(tt.sum()), "status reports the reference's num_rendered (sum of tiles_touched)"
+    for t in range(len(off) - 1):      # every super-tile list is strictly ascending in (depth bits, id)
         seg = keys[off[t]:off[t + 1]]
-        assert (np.diff(seg.astype(np.uint64).view(np.int64)) > 0).all()
+        assert (np.diff(seg.view(np.int64)) > 0).all()
     if float_exact:
         assert total == aux["num_rendered"]
-        assert np.array_equal(np.stack([off[:-1], off[1:]], 1)[aux["ranges"][:, 1] > aux["ranges"][:, 0]],
-                              aux["ranges"][aux["ranges"][:, 1] > aux["ranges"][:, 0]].astype(np.int64))
-        assert np.array_equal((keys[:total] & np.uint64(0xffffffff)).astype(np.uint32), aux["point_list"])
+        lists = _tile_lists(r)          # what the composite kernel walks == the reference's sorted tile lists
+        for t, ids in enumerate(lists):
+            r0, r1 = aux["ranges"][t]
+            assert np.array_equal(ids, aux["point_list"][r0:r1]), f"tile {t}"
     # --- images
     _close_images(color, oc, "color vs oracle")
     _close_images(depth, od, "depth vs oracle")
@@ -192,11 +210,15 @@ def test_long_tile_lists_take_the_merge_path():
     cam = _util.make_test_camera(32, 32)
     r, color, radii, depth, total, overflow = _run_cuda(g, cam, max_instances=200000)
     oc, orad, od, aux = _run_oracle(g, cam)
-    off, keys = _sorted_lists(r, 12000)
+    off, keys, rects, _ = _super_lists(r)
     assert np.diff(off).max() > 4096, "scenario must exceed one shared-memory chunk"
     for t in range(len(off) - 1):
         seg = keys[off[t]:off[t + 1]]
         assert (np.diff(seg.view(np.int64)) > 0).all()
+    if np.array_equal(radii, orad) and np.array_equal(r.intermediates()["depths"][0].cpu().numpy(), aux["depths"]):
+        for t, ids in enumerate(_tile_lists(r)):
+            r0, r1 = aux["ranges"][t]
+            assert np.array_equal(ids, aux["point_list"][r0:r1])
     _close_images(color, oc, "long lists")
     _close_images(depth, od, "long lists depth")
 
@@ -304,12 +326,14 @@ def test_full_size_properties_512():
     total, overflow = r.status()
     assert not overflow and total > 0
     it = r.intermediates()
-    off = it["tile_offset"].cpu().numpy().astype(np.int64)
-    assert off[-1] == total == int(it["tiles_touched"].sum())
-    keys = it["keys"][:total].cpu().numpy()
-    brk = np.zeros(total, bool)
-    brk[off[1:-1][off[1:-1] < total]] = True
-    assert (np.diff(keys)[~brk[1:]] > 0).all(), "every tile list strictly ascending in (depth, id)"
+    off = it["super_offset"].cpu().numpy().astype(np.int64)
+    coarse = int(off[-1])
+    assert total == int(it["tiles_touched"].sum()) and 0 < coarse <= total
+    keys = it["keys"][:coarse].cpu().numpy()
+    brk = np.zeros(coarse, bool)
+    brk[off[1:-1][off[1:-1] < coarse]] = True
+    assert (np.diff(keys)[~brk[1:]] > 0).all(), "every super-tile list strictly ascending in (depth, id)"
     assert torch.isfinite(color).all() and float(color.min()) >= 0.0
     assert float(depth.min()) > 0.0 and float(depth.max()) <= 15.0
-    print(f"R/P = {total / (B * P):.3f}, mean list length = {total / (B * (W // 16) * (H // 16)):.1f}")
+    print(f"R/P = {total / (B * P):.3f}, mean tile list = {total / (B * (W // 16) * (H // 16)):.1f}, "
+          f"(Gaussian, super-tile) instances / (Gaussian, tile) instances = {coarse / total:.3f}")

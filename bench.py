@@ -212,38 +212,62 @@ def run_ours(args):
         ms_max = ms_total
     value = world * E * args.steps / (ms_max / 1e3)
 
-    # ---- end-to-end loop: host buffers in, host buffers out, copies inside the timed region
+    # ---- end-to-end loop: host buffers in, host buffers out, copies inside the timed region.
+    # Device->host copies of step k (1.09 GB of RGB-D + particle state) run on a side stream while
+    # step k+1 computes into the other output buffer (double buffering); every byte is still moved
+    # and waited for inside the timed region.
     e2e = None
     if not args.no_e2e:
-        x_host = torch.empty((E, env.base.N, 3), dtype=torch.float32).pin_memory()
-        v_host = torch.empty_like(x_host).pin_memory()
-        color_host = torch.empty(env.color.shape, dtype=torch.float32).pin_memory()
-        depth_host = torch.empty(env.depth.shape, dtype=torch.float32).pin_memory()
+        N = env.base.N
+        hostbuf = [dict(x=torch.empty((E, N, 3)).pin_memory(), v=torch.empty((E, N, 3)).pin_memory(),
+                        color=torch.empty(env.color.shape).pin_memory(), depth=torch.empty(env.depth.shape).pin_memory())
+                   for _ in range(2)]
+        devbuf = [(env.color, env.depth), (torch.empty_like(env.color), torch.empty_like(env.depth))]
+        devstate = [(torch.empty((E, N, 3), device=dev), torch.empty((E, N, 3), device=dev)) for _ in range(2)]
         h2d = sum(t.numel() * 4 for t in acts_pinned[0]) + (env.view_h.numel() + env.proj_h.numel() + env.campos_h.numel()) * 4
-        d2h = (x_host.numel() + v_host.numel() + color_host.numel() + depth_host.numel()) * 4
+        d2h = sum(t.numel() * 4 for t in hostbuf[0].values())
+        main = torch.cuda.current_stream(dev)
+        cs = torch.cuda.Stream(dev)
+        computed = [torch.cuda.Event() for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        for ev in copied:
+            ev.record(cs)
+        phys_lib = env.phys.lib
+        import ctypes
 
-        def e2e_step(i):
-            m = upload(i)
-            env.view.copy_(env.view_h, non_blocking=True)
+        def e2e_step(i, slot):
+            m = upload(i)                                    # H2D: gripper tables (pinned -> device)
+            env.view.copy_(env.view_h, non_blocking=True)    # H2D: cameras
             env.proj.copy_(env.proj_h, non_blocking=True)
             env.campos.copy_(env.campos_h, non_blocking=True)
-            env.step(m)
-            xs, vs = env.phys.get_state()
-            x_host.copy_(xs, non_blocking=True)
-            v_host.copy_(vs, non_blocking=True)
-            color_host.copy_(env.color, non_blocking=True)
-            depth_host.copy_(env.depth, non_blocking=True)
+            main.wait_event(copied[slot])                    # the buffers of step i-2 have left the device
+            env.step(m, out=devbuf[slot])
+            xs, vs = devstate[slot]
+            _lib.check(phys_lib.r2s_phys_get_state(env.phys.h, ctypes.c_void_p(xs.data_ptr()),
+                                                   ctypes.c_void_p(vs.data_ptr()),
+                                                   ctypes.c_void_p(main.cuda_stream)), "get_state")
+            computed[slot].record(main)
+            with torch.cuda.stream(cs):                      # D2H on the side stream
+                cs.wait_event(computed[slot])
+                hb = hostbuf[slot]
+                hb["x"].copy_(xs, non_blocking=True)
+                hb["v"].copy_(vs, non_blocking=True)
+                hb["color"].copy_(devbuf[slot][0], non_blocking=True)
+                hb["depth"].copy_(devbuf[slot][1], non_blocking=True)
+                copied[slot].record(cs)
 
         base_i = args.warmup + args.steps
         for i in range(args.warmup):
-            e2e_step(base_i + i)
+            e2e_step(base_i + i, i % 2)
+        cs.synchronize()
         barrier()
-        t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(main)
         for i in range(args.steps):
-            e2e_step(base_i + args.warmup + i)
-        e1.record()
+            e2e_step(base_i + args.warmup + i, i % 2)
+        main.wait_stream(cs)                                 # all copies have landed
+        e1.record(main)
+        cs.synchronize()
         barrier()
         ms_e2e = e0.elapsed_time(e1)
         if world > 1:
@@ -251,9 +275,11 @@ def run_ours(args):
             t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms_e2e = float(t.item())
+        last = hostbuf[(args.steps - 1) % 2]
         e2e = {"value": world * E * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-               "checksum_rgb_host": float(color_host.double().sum())}
+               "overlap": "D2H of step k on a side stream under the compute of step k+1 (double-buffered outputs)",
+               "checksum_rgb_host": float(last["color"].double().sum())}
 
     # ---- metrics all-gather (the only collective)
     cx = float(env.phys.x.double().sum())
@@ -279,7 +305,7 @@ def run_ours(args):
     }
     times = {"phys_frame": phys_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
              "tile_sort": stage_ms[3], "composite": stage_ms[4]}
-    dom = max(times, key=times.get)
+    dom = max(alg, key=lambda k: times[k])   # dominant kernel among those with an algorithmic-byte model
     ach = alg[dom] / (times[dom] / 1e3) / 1e9
     kernels = {k: {"ms": round(float(v), 4), "alg_gbs": round(alg[k] / (v / 1e3) / 1e9, 1) if k in alg and v > 0 else None}
                for k, v in times.items()}

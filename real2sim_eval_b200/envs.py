@@ -159,9 +159,11 @@ class BatchedEnv:
                 _ptr(self.x0), _ptr(self.g0), _ptr(self.means3D),
                 C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "r2s_skin_translate")
 
-    def step(self, motion=None):
+    def step(self, motion=None, out=None):
         """One frame for every env: [gripper tables ->] collision graph -> substeps -> skin -> render.
-        `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None."""
+        `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None.
+        `out`: optional (color, depth) device tensors to render into (double buffering)."""
+        color, depth = out if out is not None else (self.color, self.depth)
         if self.phys.self_collision:
             self.phys.update_collision_graph()       # once per frame (phystwin.py:365-366)
         if motion is not None:
@@ -173,7 +175,7 @@ class BatchedEnv:
                             campos=self.campos, bg=self.bg, W=c.W, H=c.H, tanfovx=self.cams[0].tanfovx,
                             tanfovy=self.cams[0].tanfovy, shs=self.shs, scales=self.scales, rotations=self.rotations,
                             sh_degree=0, z_threshold=0.05, views_per_scene=c.cameras,
-                            max_instances=self.max_instances, out_color=self.color, out_depth=self.depth,
+                            max_instances=self.max_instances, out_color=color, out_depth=depth,
                             want_radii=False)
         self.frame += 1
-        return self.color, self.depth
+        return color, depth

@@ -127,6 +127,7 @@ def peaks():
 def run_ours(args):
     from real2sim_eval_b200 import _lib
     from real2sim_eval_b200.envs import BatchedEnv, EnvBatchConfig
+    from real2sim_eval_b200.shard import shard_envs
 
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
@@ -136,7 +137,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     W, H = args.res
     cfg = EnvBatchConfig(scene=args.scene, E=args.envs, W=W, H=H, cameras=args.cameras, n_substeps=args.substeps,
-                         P=args.gaussians, env_offset=rank * args.envs)
+                         P=args.gaussians, env_offset=shard_envs(world * args.envs, world, rank).start)
     env = BatchedEnv(cfg, dev)
     lib = _lib.load()
     E, ns = cfg.E, cfg.n_substeps
@@ -203,13 +204,8 @@ def run_ours(args):
     phys_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe0, pe1)]))
     lib.r2s_raster_set_profile(0)
     total, overflow = env.raster.status()
-    if world > 1:
-        import torch.distributed as dist
-        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_max = float(t.item())
-    else:
-        ms_max = ms_total
+    from real2sim_eval_b200 import shard
+    ms_max = shard.max_over_ranks(ms_total, dev)
     value = world * E * args.steps / (ms_max / 1e3)
 
     # ---- end-to-end loop: host buffers in, host buffers out, copies inside the timed region.
@@ -270,11 +266,7 @@ def run_ours(args):
         cs.synchronize()
         barrier()
         ms_e2e = e0.elapsed_time(e1)
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_e2e = float(t.item())
+        ms_e2e = shard.max_over_ranks(ms_e2e, dev)
         last = hostbuf[(args.steps - 1) % 2]
         e2e = {"value": world * E * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
@@ -284,13 +276,7 @@ def run_ours(args):
     # ---- metrics all-gather (the only collective)
     cx = float(env.phys.x.double().sum())
     crgb = float(env.color.double().sum())
-    gathered = [[args.steps, ms_total / 1e3, cx, crgb]]
-    if world > 1:
-        import torch.distributed as dist
-        mine = torch.tensor(gathered[0], device=dev, dtype=torch.float64)
-        out = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(out, mine)
-        gathered = [o.tolist() for o in out]
+    gathered = shard.gather_metrics([args.steps, ms_total / 1e3, cx, crgb], dev)
 
     # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md §8d)
     pk, pk_kind = peaks()

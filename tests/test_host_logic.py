@@ -1,0 +1,132 @@
+"""Host-side logic that needs no GPU: synthetic workload generators, camera conventions, the
+reference-compatible import shims, env sharding, and the N>1 metrics all-gather over gloo."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from real2sim_eval_b200 import shard, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_rope_graph_follows_the_reference_rule():
+    """phystwin.py:264-286 with radius 0.02 / 30 neighbours on the seeded rope: the sizes SURVEY §8d records."""
+    r = synth.make_rope()
+    assert (r.N, r.S) == (2048, 32889)
+    deg = np.bincount(r.springs.reshape(-1), minlength=r.N)
+    assert deg.min() == 29 and deg.max() == 49
+    assert len({tuple(sorted(s)) for s in r.springs.tolist()}) == r.S, "first-come de-duplication"
+    assert (r.rest > 1e-4).all()
+    posed = synth.pose_scene(r, 7)
+    assert np.array_equal(posed.springs, r.springs) and not np.array_equal(posed.rest, r.rest)
+    assert np.abs(posed.rest - r.rest).max() < 1e-6, "rest lengths differ per env only by float32 rounding"
+
+
+def test_finger_mesh_is_closed_and_outward():
+    v, f = synth.make_finger_mesh()
+    assert v.shape == (24, 3) and f.shape == (44, 3)
+    edges = {}
+    for a, b, c in f.tolist():
+        for e in ((a, b), (b, c), (c, a)):
+            edges[e] = edges.get(e, 0) + 1
+    assert all(edges.get((b, a), 0) == 1 and n == 1 for (a, b), n in edges.items()), "2-manifold, consistent winding"
+    p0, p1, p2 = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    vol = np.einsum("ij,ij->i", p0, np.cross(p1, p2)).sum() / 6.0
+    assert vol > 0, "outward orientation (positive signed volume)"
+    g = synth.make_gripper((0.5, 0.0, 0.01))
+    assert g.verts.shape == (48, 3) and g.faces.shape == (88, 3) and g.mesh_map.tolist() == [0] * 44 + [1] * 44
+
+
+def test_setup_camera_matches_the_reference_formulas():
+    """sim/utils/gs/transform_utils.py:7-31 restated with torch, as the reference computes it."""
+    import torch
+    w, h = 848, 480
+    k = np.asarray(synth.SIDE_CAM["intr"]).reshape(3, 3)
+    w2c = np.linalg.inv(np.asarray(synth.SIDE_CAM["c2w"]).reshape(4, 4))
+    cam = synth.setup_camera(w, h, k, w2c, near=0.01, far=100.0)
+    fx, fy, cx, cy = k[0][0], k[1][1], k[0][2], k[1][2]
+    t_w2c = torch.tensor(w2c).float()
+    center = torch.inverse(t_w2c)[:3, 3]
+    t_view = t_w2c.unsqueeze(0).transpose(1, 2)
+    proj = torch.tensor([[2 * fx / w, 0.0, -(w - 2 * cx) / w, 0.0], [0.0, 2 * fy / h, -(h - 2 * cy) / h, 0.0],
+                         [0.0, 0.0, 100.0 / (100.0 - 0.01), -(100.0 * 0.01) / (100.0 - 0.01)],
+                         [0.0, 0.0, 1.0, 0.0]]).float().unsqueeze(0).transpose(1, 2)
+    full = t_view.bmm(proj)
+    assert np.allclose(cam.view, t_view.reshape(-1).numpy(), atol=1e-7)
+    assert np.allclose(cam.proj, full.reshape(-1).numpy(), rtol=1e-6, atol=1e-7)
+    assert np.allclose(cam.campos, center.numpy(), atol=1e-6)
+    assert cam.tanfovx == pytest.approx(w / (2 * fx)) and cam.tanfovy == pytest.approx(h / (2 * fy))
+
+
+def test_compat_shims_expose_the_reference_names():
+    sys.path.insert(0, os.path.join(ROOT, "real2sim_eval_b200", "compat"))
+    try:
+        import importlib
+        dgr = importlib.import_module("diff_gaussian_rasterization")
+        assert dgr.GaussianRasterizationSettings._fields == (
+            "image_height", "image_width", "tanfovx", "tanfovy", "bg", "scale_modifier", "viewmatrix", "projmatrix",
+            "sh_degree", "campos", "prefiltered", "z_threshold")          # __init__.py:135-147
+        import inspect
+        sig = inspect.signature(dgr.GaussianRasterizer.forward)
+        assert list(sig.parameters)[1:] == ["means3D", "means2D", "opacities", "shs", "colors_precomp", "scales",
+                                            "rotations", "cov3D_precomp"]  # __init__.py:165
+        wp = importlib.import_module("warp")
+        for name in ("init", "set_module_options", "ScopedTimer", "to_torch", "capture_launch"):
+            assert hasattr(wp, name)
+    finally:
+        sys.path.pop(0)
+        for m in ("diff_gaussian_rasterization", "warp"):
+            sys.modules.pop(m, None)
+    from real2sim_eval_b200.physics import SpringMassSystemWarp
+    import inspect
+    params = list(inspect.signature(SpringMassSystemWarp.__init__).parameters)[1:21]
+    assert params == ["phystwin_cfg", "device", "init_vertices", "init_springs", "init_rest_lengths", "init_masses",
+                      "num_object_points", "init_spring_Y", "collide_elas", "collide_fric", "collide_eef_elas",
+                      "collide_eef_fric", "collide_self_elas", "collide_self_fric", "init_collision_mask",
+                      "init_velocities", "dynamic_meshes", "static_meshes", "dynamic_points", "use_pusher"]  # SMW:478-500
+
+
+def test_env_sharding_partitions_exactly():
+    for total, world in ((256, 1), (256, 8), (2048, 8), (10, 4), (3, 8)):
+        parts = [shard.shard_envs(total, world, r) for r in range(world)]
+        assert sorted(i for p in parts for i in p) == list(range(total))
+        assert max(len(p) for p in parts) - min(len(p) for p in parts) <= 1
+    mix = shard.interleave_scene_types({"rope": 1024, "sloth": 512, "tblock": 512}, 8)
+    assert all(len(m) == 256 and m.count("rope") == 128 and m.count("sloth") == 64 for m in mix)
+    with pytest.raises(ValueError):
+        shard.shard_envs(8, 2, 2)
+    assert shard.gather_metrics([1.0, 2.0]) == [[1.0, 2.0]] and shard.max_over_ranks(3.5) == 3.5
+
+
+_WORKER = r"""
+import os, sys, json
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from real2sim_eval_b200 import shard
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+mine = shard.shard_envs(10, world, rank)
+got = shard.gather_metrics([float(rank), float(len(mine)), float(sum(mine))])
+mx = shard.max_over_ranks(10.0 + rank)
+dist.barrier()
+if rank == 0:
+    print(json.dumps({"got": got, "max": mx}))
+dist.destroy_process_group()
+"""
+
+
+def test_metrics_allgather_world_size_2_gloo(tmp_path):
+    """The N>1 path of bench.py (shard -> run -> all-gather -> max over ranks) on CPU with gloo."""
+    import json
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT], env=dict(env, RANK=str(r)), stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    res = json.loads(outs[0][0].strip().splitlines()[-1])
+    assert res["got"] == [[0.0, 5.0, 10.0], [1.0, 5.0, 35.0]] and res["max"] == 11.0

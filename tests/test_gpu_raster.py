@@ -223,6 +223,32 @@ def test_long_tile_lists_take_the_merge_path():
     _close_images(depth, od, "long lists depth")
 
 
+def test_equal_depths_resolve_by_gaussian_id():
+    """Many Gaussians with the SAME depth bits: the stable radix sort of the reference keeps emission
+    (= id) order among them; here the bucket sort bails out (crowded bucket) and the radix path + id
+    tie-break must give the same lists."""
+    g = _util.small_gaussians(21, 900, scale=0.03)
+    g["means3D"][100:500] = g["means3D"][100]            # 400 coincident centres -> identical depth
+    g["opacities"][100:500] = 0.05
+    cam = _util.make_test_camera(64, 48)
+    r, color, radii, depth, total, _ = _run_cuda(g, cam)
+    oc, orad, od, aux = _run_oracle(g, cam)
+    dcu = r.intermediates()["depths"][0].cpu().numpy()
+    assert len(np.unique(dcu[100:500])) == 1, "the coincident Gaussians share one depth bit pattern"
+    if np.array_equal(radii, orad) and np.array_equal(dcu, aux["depths"]):
+        for t, ids in enumerate(_tile_lists(r)):
+            r0, r1 = aux["ranges"][t]
+            assert np.array_equal(ids, aux["point_list"][r0:r1]), f"tile {t}"
+    off, keys, rects, _ = _super_lists(r)
+    for t in range(len(off) - 1):
+        assert (np.diff(keys[off[t]:off[t + 1]].view(np.int64)) > 0).all(), "ties ordered by ascending id"
+    _close_images(color, oc, "equal depths")
+    if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libref_raster.so")):
+        import ref_raster
+        rc, rr, rd, n = ref_raster.forward(g, cam)
+        assert np.array_equal(color, rc) and np.array_equal(depth, rd), "bit-identical to the reference CUDA rasterizer"
+
+
 def test_batch_equals_single_views_and_shared_scene():
     """B views in one enqueue == B separate calls (bitwise); views_per_scene shares Gaussians."""
     import torch

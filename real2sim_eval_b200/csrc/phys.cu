@@ -395,8 +395,12 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
         if (has_mesh) {
             mesh.dyn = p.stage_dyn ? s_dyn : g_interp + (size_t)step * p.n_dyn * 3;
             mesh.stat = p.stat_verts; mesh.faces = p.faces; mesh.n_dyn = p.n_dyn; mesh.F = p.F;
-            // merged box of dynamic + static vertices, grown by max_dist (+ slack)
-            const float grow = 0.02f * 1.0001f + 1e-6f;
+            // merged box of dynamic + static vertices, grown by the largest contact margin (+ slack).
+            // A query can only change a particle that is inside the mesh (then it is inside the box) or
+            // closer than `margin` (5 mm fingers, 1 mm otherwise) to its surface: a hit between margin and
+            // max_dist = 20 mm has err >= 0 and leaves v unchanged and x advanced, exactly like no hit
+            // (SMW:349-351, 415-421), so those particles need no query at all.
+            const float grow = 0.005f * 1.0001f + 1e-6f;
             box_lo = f3(fminf(s_aabb[0], s_aabb[6]) - grow, fminf(s_aabb[1], s_aabb[7]) - grow,
                         fminf(s_aabb[2], s_aabb[8]) - grow);
             box_hi = f3(fmaxf(s_aabb[3], s_aabb[9]) + grow, fmaxf(s_aabb[4], s_aabb[10]) + grow,

@@ -480,12 +480,20 @@ def run_reference(args):
 
 def main():
     args = parse()
+    # Exactly ONE line may reach stdout.  Libraries (NCCL prints its version banner with printf) write to
+    # fd 1 behind Python's back, so fd 1 is pointed at stderr for the whole run and the JSON line goes to
+    # a saved copy of the real stdout.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         line = run_reference(args)
     else:
         line = run_ours(args)
+    sys.stdout.flush()
     if line is not None:
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    os.close(real_stdout)
 
 
 if __name__ == "__main__":

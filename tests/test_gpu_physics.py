@@ -235,3 +235,39 @@ def test_full_size_properties_256_envs():
     o = _util.oracle_from_scene(base, 10)
     o.update_collision_graph(); o.step()
     assert np.abs(x[17].cpu().numpy() - o.x).max() <= TIGHT_X
+
+
+def test_large_scene_uses_the_global_state_kernel():
+    """N = 6000 particles (> 227 KB of float4 state): the frame kernel keeps x/v in HBM/L2 instead of
+    shared memory (frame_kernel<.., kSmemState=false>) and must give the same answer."""
+    rng = np.random.default_rng(5)
+    n = 6000
+    pts = np.stack([rng.uniform(0, 0.3, n), rng.uniform(0, 0.3, n), rng.uniform(0.01, 0.06, n)], 1).astype(np.float32)
+    springs, rest = synth.build_springs(pts.astype(np.float64), pts.astype(np.float64), 0.012, 12)
+    v = rng.uniform(-0.05, 0.05, pts.shape).astype(np.float32)
+    sc = synth.Scene("blob", pts, v, springs, rest, np.full(len(springs), np.log(np.float32(3e4)), np.float32),
+                     np.ones(n, np.float32), dict(synth.DEFAULT_PARAMS))
+    o = _util.oracle_from_scene(sc, 8)
+    c = _util.cuda_from_scenes([sc, sc], 8, per_env_rest=False)
+    assert not c.smem_state
+    o.update_collision_graph(); c.update_collision_graph()
+    assert np.array_equal(c.coll_num[1].cpu().numpy(), o.coll_num)
+    o.step(); c.step()
+    _cmp(c, [o, o], tol_x=TIGHT_X, tol_v=2e-2, outlier_frac=0.01, hard_x=1e-3)
+
+
+def test_parameter_setters_and_reverse_z():
+    """set_spring_Y / set_collide after construction (SMW:946-995) and reverse_z (gravity and ground flipped)."""
+    sc = synth.make_chain(n=16, z=-0.0006)
+    sc.v[:] = [0.1, 0.0, 0.4]
+    kw = dict(self_collision=False, reverse_z=True)
+    o = _util.oracle_from_scene(sc, 30, **{k: v for k, v in kw.items() if k != "reverse_z"}, reverse_z=True)
+    c = _util.cuda_from_scenes([sc], 30, **kw)
+    newY = np.log(np.linspace(2e4, 2e5, sc.S).astype(np.float32))      # partly above Y_max -> clamped
+    o.log_Y[:] = newY
+    c.set_spring_Y(newY)
+    o.s.collide_elas, o.s.collide_fric = 0.8, 0.1
+    c.set_collide(elas=0.8, fric=0.1)
+    o.step(); c.step()
+    x, _ = _cmp(c, [o])
+    assert (x[0][:, 2] < 1e-7).all(), "with reverse_z the ground is above: z stays <= 0"

@@ -365,3 +365,17 @@ def test_full_size_properties_512():
     assert float(depth.min()) > 0.0 and float(depth.max()) <= 15.0
     print(f"R/P = {total / (B * P):.3f}, mean tile list = {total / (B * (W // 16) * (H // 16)):.1f}, "
           f"(Gaussian, super-tile) instances / (Gaussian, tile) instances = {coarse / total:.3f}")
+
+
+def test_scale_modifier_and_prefiltered_flag():
+    g = _util.small_gaussians(31, 900)
+    cam = _util.make_test_camera(72, 56)
+    from oracle import raster_ref
+    _, color, radii, depth, _, _ = _run_cuda(g, cam, scale_modifier=1.7, prefiltered=False)
+    oc, orad, od = raster_ref.rasterize(g["means3D"], g["opacities"], viewmatrix=cam.view, projmatrix=cam.proj,
+                                        campos=cam.campos, bg=np.zeros(3, np.float32), W=cam.W, H=cam.H,
+                                        tanfovx=cam.tanfovx, tanfovy=cam.tanfovy, shs=g["shs"], scales=g["scales"],
+                                        rotations=g["rotations"], scale_modifier=1.7, z_threshold=cam.z_threshold)
+    assert (radii == orad).mean() > 0.995 and radii.max() > 0
+    _close_images(color, oc, "scale_modifier 1.7")
+    _close_images(depth, od, "scale_modifier 1.7 depth")

@@ -9,7 +9,7 @@
 Workload (BASELINE.json configs[1]): rope PhysTwin (synthetic, N=2048 particles / S=32889
 springs), 256 parallel envs per GPU, 10 substeps per step, one 512x512 RGB-D render per env of
 200,000 Gaussians (10% bound to the particles).  A step is one pass of the hot path over all
-envs: per-frame collision-graph rebuild -> 10 substeps -> re-bind object Gaussians -> render.
+envs: per-frame collision-graph rebuild -> 10 substeps -> LBS of the object Gaussians -> render.
 Multi-GPU: envs shard statically, one process per GPU, no data-path collective; one NCCL
 all-gather of {steps, seconds, checksum(x), checksum(rgb)} at the end (weak scaling).
 
@@ -185,10 +185,11 @@ def run_ours(args):
         if env.phys.self_collision:
             env.phys.update_collision_graph()
         env.phys.set_mesh_motion(*m)
+        env.x_prev4.copy_(env.phys.x4)
         pe0[k].record()
         env.phys.step()
         pe1[k].record()
-        env._skin()
+        env.lbs.forward(env.x_prev4, env.phys.x4, env.means3D)
         env.raster.forward(env.means3D, env.opacities, viewmatrix=env.view, projmatrix=env.proj, campos=env.campos,
                            bg=env.bg, W=W, H=H, tanfovx=env.cams[0].tanfovx, tanfovy=env.cams[0].tanfovy, shs=env.shs,
                            scales=env.scales, rotations=env.rotations, sh_degree=0, z_threshold=0.05,

@@ -113,15 +113,6 @@ int r2s_raster_workspace_layout(int32_t B, int32_t P, int32_t W, int32_t H, int6
 int r2s_raster_set_profile(int32_t enable);
 int r2s_raster_get_profile(float ms[R2S_RASTER_STAGES]);
 
-/* Translation-only skinning of the object Gaussians onto the particles (the stand-in for the
- * reference's LBS step between physics and render, sim/renderer/gs_renderer.py:732-749 --
- * SURVEY.md §8f row N1; rotations are NOT updated).  For env e and object Gaussian g:
- *   means3D[e, g] = g0[g] + sum_k w[g,k] * (x4[e, idx[g,k]].xyz - x0[idx[g,k]])
- * x4 is the physics state [E,N,4]; means3D is [E,P,3] (rows >= n_obj untouched). */
-int r2s_skin_translate(int32_t E, int32_t N, int32_t P, int32_t n_obj, int32_t K, const int32_t* idx,
-                       const float* w, const float* x4, const float* x0, const float* g0, float* means3D,
-                       void* stream);
-
 #ifdef __cplusplus
 }
 #endif

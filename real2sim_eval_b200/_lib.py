@@ -53,6 +53,14 @@ class RasterArgs(C.Structure):  # include/r2s_raster.h: r2s_raster_args
     ]
 
 
+class LbsArgs(C.Structure):  # include/r2s_lbs.h: r2s_lbs_args
+    _fields_ = [
+        ("E", c_i32), ("N", c_i32), ("P", c_i32), ("n_obj", c_i32), ("k_rel", c_i32), ("k_wgt", c_i32),
+        ("relations", c_vp), ("weights_indices", c_vp), ("weights", c_vp), ("bones4", c_vp), ("bones_new4", c_vp),
+        ("means3D", c_vp), ("rot_scratch", c_vp), ("rank_flags", c_vp),
+    ]
+
+
 class RasterLayout(C.Structure):  # r2s_raster_layout
     _fields_ = [(n, c_sz) for n in ("status", "depths", "radii", "tiles_touched", "rec_a", "rec_b", "rec_c", "rects",
                                     "tile_count", "tile_offset", "tile_fill", "keys", "keys_alt", "sorted_rect",
@@ -86,7 +94,7 @@ SYMBOLS = [
     ("r2s_mark_visible", C.c_int, [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]),
     ("r2s_raster_set_profile", C.c_int, [c_i32]),
     ("r2s_raster_get_profile", C.c_int, [C.POINTER(c_f * 5)]),
-    ("r2s_skin_translate", C.c_int, [c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    ("r2s_lbs_forward", C.c_int, [C.POINTER(LbsArgs), c_vp]),
 ]
 
 _lib = None

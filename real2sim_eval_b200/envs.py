@@ -4,8 +4,9 @@ particles, one render per (env, camera) -- without a host synchronisation.
 
 This is the per-frame sequence of the reference's BaseEnv.step + get_obs
 (sim/envs/env.py:86-94, 53-74: physics.step -> renderer.update_state -> render)
-restricted to the two hot paths this repository implements; the LBS step between
-them is the translation-only stand-in of r2s_skin_translate.
+restricted to the two hot paths this repository implements plus the LBS step between
+them (r2s_lbs_forward: `interpolate_motions`, sim/utils/gs/transform_utils.py:58-212, as
+sim/renderer/gs_renderer.py:732-749 calls it -- SURVEY.md §8f N1).
 All device work goes to torch's current stream.
 """
 from __future__ import annotations
@@ -17,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, synth
+from .lbs import BatchedLBS
 from .physics import BatchedSpringMass
 from .rasterizer import BatchedRasterizer
 
@@ -35,7 +37,8 @@ class EnvBatchConfig:
     n_substeps: int = 10
     P: int = 200_000             # Gaussians per environment
     obj_frac: float = 0.1        # fraction bound to the particles
-    knn: int = 16
+    knn: int = 16                # bones per Gaussian (gs_renderer.py:35 k_wgt)
+    k_rel: int = 8               # neighbours per bone (gs_renderer.py:34 k_rel)
     seed: int = 1234
     env_offset: int = 0          # global index of this shard's first env (multi-GPU sharding)
     gripper: bool = True
@@ -62,6 +65,7 @@ class BatchedEnv:
         E = cfg.E
         base = _scene(cfg.scene)
         self.base = base
+        pose_tf = [synth.pose_transform(base, cfg.seed + cfg.env_offset + e) for e in range(E)]
         poses = [synth.pose_scene(base, cfg.seed + cfg.env_offset + e) for e in range(E)]
         rest = np.stack([p.rest for p in poses])
         pr = dict(base.params)
@@ -92,18 +96,17 @@ class BatchedEnv:
         shs = torch.empty((E, P, 1, 3), device=dev)
         lo = torch.tensor([-0.1, -0.6, 0.0], device=dev)
         hi = torch.tensor([1.1, 0.6, 0.6], device=dev)
-        # object Gaussians share their binding (idx, weights, rest offsets) across envs: one PhysTwin, E poses
+        # object Gaussians share their binding (relations, weights: invariant under each env's rigid pose)
         rng = np.random.default_rng(cfg.seed)
         from scipy.spatial import cKDTree
         src = base.x[rng.integers(0, base.N, n_obj)].astype(np.float64) + rng.normal(0, 0.002, (n_obj, 3))
-        dist, idx = cKDTree(base.x).query(src, k=self.K)
-        idx = idx.reshape(n_obj, self.K)
-        w = 1.0 / np.maximum(dist.reshape(n_obj, self.K), 1e-6)
+        tree = cKDTree(base.x)
+        dist, idx = tree.query(src, k=self.K)                      # gs_renderer.py:202-211 knn_weights
+        w = 1.0 / (dist.reshape(n_obj, self.K).astype(np.float32) + np.float32(1e-6))
         w = (w / w.sum(1, keepdims=True)).astype(np.float32)
-        self.bind_idx = torch.tensor(idx.astype(np.int32), device=dev)
-        self.bind_w = torch.tensor(w, device=dev)
-        self.g0 = torch.tensor(src.astype(np.float32), device=dev)
-        self.x0 = torch.tensor(base.x, device=dev)
+        rel = tree.query(base.x, k=cfg.k_rel + 1)[1][:, 1:]        # gs_renderer.py:195-200 knn_relations
+        self.lbs = BatchedLBS(E, base.N, P, n_obj, rel, w, idx.reshape(n_obj, self.K), device=dev)
+        self.x_prev4 = torch.empty_like(self.phys.x4)
         for e in range(E):
             gen.manual_seed(cfg.seed + 7 * (cfg.env_offset + e) + 1)
             means[e] = lo + (hi - lo) * torch.rand((P, 3), device=dev, generator=gen)
@@ -112,6 +115,7 @@ class BatchedEnv:
             rots[e] = q / q.norm(dim=1, keepdim=True)
             opac[e] = torch.sigmoid(1.5 + 1.5 * torch.randn((P, 1), device=dev, generator=gen))
             shs[e] = (torch.rand((P, 1, 3), device=dev, generator=gen) - 0.5) / 0.28209479177387814
+            means[e, :n_obj] = torch.tensor(synth.pose_points(src, pose_tf[e]), device=dev)   # posed with the env's object
         self.means3D, self.scales, self.rotations, self.opacities, self.shs = means, scales, rots, opac, shs
         # cameras: cfg.cameras fixed views per env (side, and a top-down second view), small per-env jitter
         cams = []
@@ -131,7 +135,6 @@ class BatchedEnv:
         self.color = torch.empty((self.B, 3, cfg.H, cfg.W), device=dev)
         self.depth = torch.empty((self.B, 1, cfg.H, cfg.W), device=dev)
         self.frame = 0
-        self._skin()
 
     # ---- per-frame host-side action -> gripper motion tables (numpy, pinned by the caller if needed)
     def make_actions(self, frame: int):
@@ -151,14 +154,6 @@ class BatchedEnv:
         self.finger_pose = self.finger_pose + vel * np.float32(self.dt * ns)
         return pts, ctr, dyn_vel, dyn_omega
 
-    def _skin(self):
-        c, dev = self.cfg, self.device
-        with torch.cuda.device(dev):
-            _lib.check(self.lib.r2s_skin_translate(
-                c.E, self.base.N, c.P, self.n_obj, self.K, _ptr(self.bind_idx), _ptr(self.bind_w), _ptr(self.phys.x4),
-                _ptr(self.x0), _ptr(self.g0), _ptr(self.means3D),
-                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "r2s_skin_translate")
-
     def step(self, motion=None, out=None):
         """One frame for every env: [gripper tables ->] collision graph -> substeps -> skin -> render.
         `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None.
@@ -168,8 +163,9 @@ class BatchedEnv:
             self.phys.update_collision_graph()       # once per frame (phystwin.py:365-366)
         if motion is not None:
             self.phys.set_mesh_motion(*motion)
+        self.x_prev4.copy_(self.phys.x4)             # state['x'] before the frame (gs_renderer.py:727)
         self.phys.step()
-        self._skin()
+        self.lbs.forward(self.x_prev4, self.phys.x4, self.means3D)
         c = self.cfg
         self.raster.forward(self.means3D, self.opacities, viewmatrix=self.view, projmatrix=self.proj,
                             campos=self.campos, bg=self.bg, W=c.W, H=c.H, tanfovx=self.cams[0].tanfovx,

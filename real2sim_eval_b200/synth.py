@@ -153,18 +153,27 @@ def make_chain(n: int = 8, spacing: float = 0.01, z: float = 0.05, Y: float = 3e
                  np.ones(n, dtype=np.float32), dict(DEFAULT_PARAMS))
 
 
-def pose_scene(scene: Scene, seed: int) -> Scene:
-    """Clone ``scene`` under a small seeded rigid pose (yaw + xy shift), as each
-    parallel env randomises its object pose; rest lengths are recomputed in
-    float32 from the posed cloud, so they differ per env (SURVEY §7 sizing note)."""
+def pose_transform(scene: Scene, seed: int):
+    """Seeded rigid pose of an env's object: (R (3,3), centre (3,), shift (3,)); p -> (p - centre) R^T + centre + shift."""
     rng = np.random.default_rng(seed)
     yaw = rng.uniform(-0.3, 0.3)
     sh = rng.uniform(-0.02, 0.02, 2)
     c, s = np.cos(yaw), np.sin(yaw)
     R = np.array([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
-    ctr = scene.x.astype(np.float64).mean(0)
-    x = (scene.x.astype(np.float64) - ctr) @ R.T + ctr + np.array([sh[0], sh[1], 0.0])
-    x = x.astype(np.float32)
+    return R, scene.x.astype(np.float64).mean(0), np.array([sh[0], sh[1], 0.0])
+
+
+def pose_points(pts: np.ndarray, pose) -> np.ndarray:
+    R, ctr, shift = pose
+    return ((np.asarray(pts, np.float64) - ctr) @ R.T + ctr + shift).astype(np.float32)
+
+
+def pose_scene(scene: Scene, seed: int) -> Scene:
+    """Clone ``scene`` under a small seeded rigid pose (yaw + xy shift), as each
+    parallel env randomises its object pose; rest lengths are recomputed in
+    float32 from the posed cloud, so they differ per env (SURVEY §7 sizing note)."""
+    R, ctr, shift = pose_transform(scene, seed)
+    x = pose_points(scene.x, (R, ctr, shift))
     v = (scene.v.astype(np.float64) @ R.T).astype(np.float32)
     return Scene(scene.name, x, v, scene.springs, rest_lengths_f32(x, scene.springs), scene.log_Y,
                  scene.mass, dict(scene.params))

@@ -37,14 +37,15 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_ctypes_struct_mirrors_match_the_c_headers(tmp_path):
     from real2sim_eval_b200 import _lib
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "r2s_phys.h"\n#include "r2s_raster.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu\\n", sizeof(r2s_phys_desc), sizeof(r2s_phys_ptrs),'
-                   ' sizeof(r2s_raster_args), sizeof(r2s_raster_layout)); return 0;}\n')
+    src.write_text('#include <stdio.h>\n#include "r2s_phys.h"\n#include "r2s_raster.h"\n#include "r2s_lbs.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu\\n", sizeof(r2s_phys_desc), sizeof(r2s_phys_ptrs),'
+                   ' sizeof(r2s_raster_args), sizeof(r2s_raster_layout), sizeof(r2s_lbs_args)); return 0;}\n')
     exe = tmp_path / "sz"
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([cc, "-I", INC, str(src), "-o", str(exe)], check=True)   # the headers are plain C
     got = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
-    want = [C.sizeof(_lib.PhysDesc), C.sizeof(_lib.PhysPtrs), C.sizeof(_lib.RasterArgs), C.sizeof(_lib.RasterLayout)]
+    want = [C.sizeof(_lib.PhysDesc), C.sizeof(_lib.PhysPtrs), C.sizeof(_lib.RasterArgs), C.sizeof(_lib.RasterLayout),
+            C.sizeof(_lib.LbsArgs)]
     assert got == want
 
 
@@ -61,7 +62,7 @@ def test_argument_validation_reports_through_last_error():
     d = _lib.PhysDesc()
     assert not lib.r2s_phys_create(C.byref(d)) and b"bad descriptor" in lib.r2s_last_error()
     assert lib.r2s_raster_get_profile(None) == -1
-    assert lib.r2s_skin_translate(0, 0, 0, 0, 0, None, None, None, None, None, None, None) == -1
+    assert lib.r2s_lbs_forward(None, None) == -1 and b"null args" in lib.r2s_last_error()
 
 
 def test_workspace_layout_arithmetic():

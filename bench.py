@@ -176,6 +176,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     pe0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     pe1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pe2 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     import ctypes
     prof = (ctypes.c_float * 5)()
     ev0.record()
@@ -190,6 +191,7 @@ def run_ours(args):
         env.phys.step()
         pe1[k].record()
         env.lbs.forward(env.x_prev4, env.phys.x4, env.means3D)
+        pe2[k].record()
         env.raster.forward(env.means3D, env.opacities, viewmatrix=env.view, projmatrix=env.proj, campos=env.campos,
                            bg=env.bg, W=W, H=H, tanfovx=env.cams[0].tanfovx, tanfovy=env.cams[0].tanfovy, shs=env.shs,
                            scales=env.scales, rotations=env.rotations, sh_degree=0, z_threshold=0.05,
@@ -203,6 +205,7 @@ def run_ours(args):
     _lib.check(lib.r2s_raster_get_profile(prof), "get_profile")   # stages of the LAST timed step
     stage_ms = np.array(list(prof), dtype=np.float64)
     phys_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe0, pe1)]))
+    lbs_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe1, pe2)]))
     lib.r2s_raster_set_profile(0)
     total, overflow = env.raster.status()
     from real2sim_eval_b200 import shard
@@ -285,12 +288,13 @@ def run_ours(args):
     R = total
     alg = {
         "phys_frame": E * ns * (52 * env.base.N + 16 * env.base.S),
+        "lbs": E * env.base.N * (32 + 36) + E * env.n_obj * 24 + env.n_obj * env.K * 8 + env.base.N * cfg.k_rel * 4,
         "preprocess": B * P * (44 + 12 * 1) + B * P * 40,
         "emit": R * 12,
         "tile_sort": R * 24,
         "composite": R * 40 + B * W * H * 16,
     }
-    times = {"phys_frame": phys_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
+    times = {"phys_frame": phys_ms, "lbs": lbs_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
              "tile_sort": stage_ms[3], "composite": stage_ms[4]}
     dom = max(alg, key=lambda k: times[k])   # dominant kernel among those with an algorithmic-byte model
     ach = alg[dom] / (times[dom] / 1e3) / 1e9

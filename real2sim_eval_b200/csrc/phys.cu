@@ -22,6 +22,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -294,12 +295,22 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
         for (int i = grp; i < N; i += n_groups) {
             const float4 xi4 = sx[i], vi4 = sv[i];
             const float3 xi = xyz(xi4), vi = xyz(vi4);
-            const int beg = p.row_ptr[i], end = p.row_ptr[i + 1];
+            const int beg = __ldg(p.row_ptr + i), end = __ldg(p.row_ptr + i + 1);
             float3 acc = f3(0.f, 0.f, 0.f);
-            for (int k = beg + lane_g; k < end; k += G) {
-                const int2 nk = __ldg(p.nbr_k + k);
+            // software pipeline: the {neighbour, stiffness} / rest-length loads of trip t+1 (L2 / HBM) are
+            // issued before the arithmetic of trip t
+            int k = beg + lane_g;
+            bool have = k < end;
+            int2 nk_next = make_int2(0, 0);
+            float r_next = 1.0f;
+            if (have) { nk_next = __ldg(p.nbr_k + k); r_next = __ldg(rest + k); }
+            while (have) {
+                const int2 nk = nk_next;
+                const float r = r_next;
+                k += G;
+                have = k < end;
+                if (have) { nk_next = __ldg(p.nbr_k + k); r_next = __ldg(rest + k); }
                 const float kk = __int_as_float(nk.y);
-                const float r = __ldg(rest + k);
                 if (kk >= 0.0f) {  // exp(Y) > Y_min guard (SMW:75), resolved at set_spring_Y time
                     const float3 xj = xyz(sx[nk.x]), vj = xyz(sv[nk.x]);
                     const float3 dis = xj - xi;
@@ -1109,6 +1120,11 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     p.dynvel_stride = pe * 6;
     p.omega_stride = pe * 3;
     p.coll_forces = h->coll_forces;
+    // lanes per adjacency row: 8 suits degrees ~30-60; R2S_PHYS_G overrides it for tuning
+    static const int g_lanes = [] { const char* e = getenv("R2S_PHYS_G"); return e ? atoi(e) : 8; }();
+    if (g_lanes == 4) return launch_frame<4>(h, p, st);
+    if (g_lanes == 16) return launch_frame<16>(h, p, st);
+    if (g_lanes == 32) return launch_frame<32>(h, p, st);
     return launch_frame<8>(h, p, st);
 }
 

@@ -81,7 +81,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.t0 = gpu_index, None, [], 0.0
 
     def start(self):
         try:
@@ -93,7 +93,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Samples arriving from now on count as 'under load' (call right before the measured span)."""
+        self.t0 = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -101,7 +105,9 @@ class ClockSampler:
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for t, ln in self.lines:
+            if t < self.t0:
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -163,6 +169,8 @@ def run_ours(args):
     motions_dev = [tuple(t.to(dev) for t in act) for act in acts_pinned[:args.warmup + args.steps]]
     sampler = ClockSampler(local)   # samples clocks / throttle reasons from the warm-up through the e2e loop
     sampler.start()
+    time.sleep(1.0)                 # let nvidia-smi start streaming before the measured span
+    sampler.mark()
     for i in range(args.warmup):
         env.step(motions_dev[i])
     total, overflow = env.raster.status()
@@ -453,6 +461,8 @@ def run_reference(args):
         step()
     sampler = ClockSampler(local)
     sampler.start()
+    time.sleep(1.0)
+    sampler.mark()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         rendered = step()

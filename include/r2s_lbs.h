@@ -36,7 +36,8 @@ typedef struct r2s_lbs_args {
     const float* bones4;            /* [E, N, 4] particle positions BEFORE the frame (state['x'])  */
     const float* bones_new4;        /* [E, N, 4] particle positions AFTER the frame (x_pred)       */
     float* means3D;                 /* [E, P, 3] in/out: rows < n_obj are transformed in place     */
-    float* rot_scratch;             /* [E, N, 9] bone rotations (caller-owned scratch)             */
+    float* rot_scratch;             /* [E, N, 12] bone transforms [R | new - R old] as three float4 rows;
+                                       caller-owned scratch, 16-byte aligned                       */
     int32_t* rank_flags;            /* [E] out: 1 if every bone had rank >= 2, else 0 (identity used) */
 } r2s_lbs_args;
 

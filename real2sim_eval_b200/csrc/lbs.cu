@@ -121,9 +121,12 @@ __global__ void lbs_rotation_kernel(const r2s_lbs_args a)
     } else {
         atomicAnd(a.rank_flags + e, 0);
     }
-    float* out = a.rot_scratch + (size_t)t * 9;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) out[k] = R[k];
+    // bone transform as three float4 rows [R | c], c = new - R old, so that the blend is sum_k w_k (R x + c):
+    // algebraically the reference's R (x - old) + motion + old
+    float4* out = reinterpret_cast<float4*>(a.rot_scratch) + (size_t)t * 3;
+    out[0] = make_float4(R[0], R[1], R[2], n0.x - (R[0] * o0.x + R[1] * o0.y + R[2] * o0.z));
+    out[1] = make_float4(R[3], R[4], R[5], n0.y - (R[3] * o0.x + R[4] * o0.y + R[5] * o0.z));
+    out[2] = make_float4(R[6], R[7], R[8], n0.z - (R[6] * o0.x + R[7] * o0.y + R[8] * o0.z));
 }
 
 __global__ void lbs_flag_reset_kernel(int* flags, int E)
@@ -132,7 +135,8 @@ __global__ void lbs_flag_reset_kernel(int* flags, int E)
     if (e < E) flags[e] = 1;
 }
 
-// One thread per (env, Gaussian): xyz' = sum_k w_k (R_b (xyz - bone_b) + motion_b + bone_b).
+// One thread per (env, Gaussian): xyz' = sum_k w_k (R_b (xyz - bone_b) + motion_b + bone_b), evaluated as
+// sum_k w_k (R_b xyz + c_b) with c_b = new_b - R_b old_b from the rotation kernel (three 16-byte loads per bone).
 __global__ void lbs_blend_kernel(const r2s_lbs_args a)
 {
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -140,27 +144,28 @@ __global__ void lbs_blend_kernel(const r2s_lbs_args a)
     const int e = (int)(t / a.n_obj), g = (int)(t % a.n_obj);
     const float4* b0 = reinterpret_cast<const float4*>(a.bones4) + (size_t)e * a.N;
     const float4* b1 = reinterpret_cast<const float4*>(a.bones_new4) + (size_t)e * a.N;
-    const float* Rm = a.rot_scratch + (size_t)e * a.N * 9;
+    const float4* Rm = reinterpret_cast<const float4*>(a.rot_scratch) + (size_t)e * a.N * 3;
     const bool use_R = a.rank_flags[e] != 0;   // reference quirk: one deficient bone -> identity for all
     float* x = a.means3D + ((size_t)e * a.P + g) * 3;
     const float px = x[0], py = x[1], pz = x[2];
     float ox = 0.f, oy = 0.f, oz = 0.f;
+    const int* wi = a.weights_indices + (size_t)g * a.k_wgt;
+    const float* ww = a.weights + (size_t)g * a.k_wgt;
     for (int k = 0; k < a.k_wgt; ++k) {
-        const int b = a.weights_indices[(size_t)g * a.k_wgt + k];
-        const float wk = a.weights[(size_t)g * a.k_wgt + k];
-        const float4 o = b0[b], n = b1[b];
-        const float dx = px - o.x, dy = py - o.y, dz = pz - o.z;
-        float tx = dx, ty = dy, tz = dz;
+        const int b = __ldg(wi + k);
+        const float wk = __ldg(ww + k);
+        float tx, ty, tz;
         if (use_R) {
-            const float* R = Rm + (size_t)b * 9;
-            tx = R[0] * dx + R[1] * dy + R[2] * dz;
-            ty = R[3] * dx + R[4] * dy + R[5] * dz;
-            tz = R[6] * dx + R[7] * dy + R[8] * dz;
+            const float4 r0 = Rm[3 * b], r1 = Rm[3 * b + 1], r2 = Rm[3 * b + 2];
+            tx = r0.x * px + r0.y * py + r0.z * pz + r0.w;
+            ty = r1.x * px + r1.y * py + r1.z * pz + r1.w;
+            tz = r2.x * px + r2.y * py + r2.z * pz + r2.w;
+        } else {
+            const float4 o = b0[b], n = b1[b];
+            tx = (px - o.x) + (n.x - o.x) + o.x;
+            ty = (py - o.y) + (n.y - o.y) + o.y;
+            tz = (pz - o.z) + (n.z - o.z) + o.z;
         }
-        // + motion_b + bone_b, in the reference's order (transform_utils.py:187)
-        tx = tx + (n.x - o.x) + o.x;
-        ty = ty + (n.y - o.y) + o.y;
-        tz = tz + (n.z - o.z) + o.z;
         ox += tx * wk; oy += ty * wk; oz += tz * wk;
     }
     x[0] = ox; x[1] = oy; x[2] = oz;

@@ -33,7 +33,7 @@ class BatchedLBS:
         self.weights_indices = as_t(weights_indices, torch.int32)
         assert self.relations.shape[0] == self.N and self.weights.shape == self.weights_indices.shape
         assert self.weights.shape[0] == self.n_obj
-        self.rot = torch.empty((self.E, self.N, 9), dtype=torch.float32, device=dev)
+        self.rot = torch.empty((self.E, self.N, 12), dtype=torch.float32, device=dev)
         self.rank_flags = torch.ones(self.E, dtype=torch.int32, device=dev)
 
     def forward(self, bones4, bones_new4, means3D):

@@ -135,40 +135,50 @@ __global__ void lbs_flag_reset_kernel(int* flags, int E)
     if (e < E) flags[e] = 1;
 }
 
-// One thread per (env, Gaussian): xyz' = sum_k w_k (R_b (xyz - bone_b) + motion_b + bone_b), evaluated as
-// sum_k w_k (R_b xyz + c_b) with c_b = new_b - R_b old_b from the rotation kernel (three 16-byte loads per bone).
-__global__ void lbs_blend_kernel(const r2s_lbs_args a)
+// xyz' = sum_k w_k (R_b (xyz - bone_b) + motion_b + bone_b), evaluated as sum_k w_k (R_b xyz + c_b) with
+// c_b = new_b - R_b old_b from the rotation kernel.  grid = (chunks of Gaussians, E): a block first stages its
+// environment's N bone transforms (48 B each) in shared memory with coalesced 16-byte loads, then every thread
+// gathers its k_wgt bones from there; kStage = false reads them from global memory (N too large to stage).
+template <bool kStage>
+__global__ void lbs_blend_kernel(const r2s_lbs_args a, int per_block)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= (long long)a.E * a.n_obj) return;
-    const int e = (int)(t / a.n_obj), g = (int)(t % a.n_obj);
-    const float4* b0 = reinterpret_cast<const float4*>(a.bones4) + (size_t)e * a.N;
-    const float4* b1 = reinterpret_cast<const float4*>(a.bones_new4) + (size_t)e * a.N;
+    extern __shared__ float4 s_T[];  // [N][3]
+    const int e = blockIdx.y;
     const float4* Rm = reinterpret_cast<const float4*>(a.rot_scratch) + (size_t)e * a.N * 3;
     const bool use_R = a.rank_flags[e] != 0;   // reference quirk: one deficient bone -> identity for all
-    float* x = a.means3D + ((size_t)e * a.P + g) * 3;
-    const float px = x[0], py = x[1], pz = x[2];
-    float ox = 0.f, oy = 0.f, oz = 0.f;
-    const int* wi = a.weights_indices + (size_t)g * a.k_wgt;
-    const float* ww = a.weights + (size_t)g * a.k_wgt;
-    for (int k = 0; k < a.k_wgt; ++k) {
-        const int b = __ldg(wi + k);
-        const float wk = __ldg(ww + k);
-        float tx, ty, tz;
-        if (use_R) {
-            const float4 r0 = Rm[3 * b], r1 = Rm[3 * b + 1], r2 = Rm[3 * b + 2];
-            tx = r0.x * px + r0.y * py + r0.z * pz + r0.w;
-            ty = r1.x * px + r1.y * py + r1.z * pz + r1.w;
-            tz = r2.x * px + r2.y * py + r2.z * pz + r2.w;
-        } else {
-            const float4 o = b0[b], n = b1[b];
-            tx = (px - o.x) + (n.x - o.x) + o.x;
-            ty = (py - o.y) + (n.y - o.y) + o.y;
-            tz = (pz - o.z) + (n.z - o.z) + o.z;
-        }
-        ox += tx * wk; oy += ty * wk; oz += tz * wk;
+    if (kStage && use_R) {
+        for (int k = threadIdx.x; k < 3 * a.N; k += blockDim.x) s_T[k] = Rm[k];
+        __syncthreads();
     }
-    x[0] = ox; x[1] = oy; x[2] = oz;
+    const float4* T = (kStage && use_R) ? s_T : Rm;
+    const float4* b0 = reinterpret_cast<const float4*>(a.bones4) + (size_t)e * a.N;
+    const float4* b1 = reinterpret_cast<const float4*>(a.bones_new4) + (size_t)e * a.N;
+    const int g_end = min(a.n_obj, (int)(blockIdx.x + 1) * per_block);
+    for (int g = blockIdx.x * per_block + threadIdx.x; g < g_end; g += blockDim.x) {
+        float* x = a.means3D + ((size_t)e * a.P + g) * 3;
+        const float px = x[0], py = x[1], pz = x[2];
+        float ox = 0.f, oy = 0.f, oz = 0.f;
+        const int* wi = a.weights_indices + (size_t)g * a.k_wgt;
+        const float* ww = a.weights + (size_t)g * a.k_wgt;
+        for (int k = 0; k < a.k_wgt; ++k) {
+            const int b = __ldg(wi + k);
+            const float wk = __ldg(ww + k);
+            float tx, ty, tz;
+            if (use_R) {
+                const float4 r0 = T[3 * b], r1 = T[3 * b + 1], r2 = T[3 * b + 2];
+                tx = r0.x * px + r0.y * py + r0.z * pz + r0.w;
+                ty = r1.x * px + r1.y * py + r1.z * pz + r1.w;
+                tz = r2.x * px + r2.y * py + r2.z * pz + r2.w;
+            } else {
+                const float4 o = b0[b], n = b1[b];
+                tx = (px - o.x) + (n.x - o.x) + o.x;
+                ty = (py - o.y) + (n.y - o.y) + o.y;
+                tz = (pz - o.z) + (n.z - o.z) + o.z;
+            }
+            ox += tx * wk; oy += ty * wk; oz += tz * wk;
+        }
+        x[0] = ox; x[1] = oy; x[2] = oz;
+    }
 }
 
 }  // namespace
@@ -188,7 +198,15 @@ extern "C" int r2s_lbs_forward(const r2s_lbs_args* a, void* stream)
     lbs_rotation_kernel<<<r2s::ceil_div((long long)a->E * a->N, 128), 128, 0, st>>>(*a);
     R2S_LAUNCH_CHECK();
     if (a->n_obj > 0) {
-        lbs_blend_kernel<<<r2s::ceil_div((long long)a->E * a->n_obj, 256), 256, 0, st>>>(*a);
+        const size_t smem = sizeof(float4) * 3 * (size_t)a->N;
+        const int per_block = 2048;  // Gaussians per block: amortises the staging of N transforms
+        const dim3 grid(r2s::ceil_div(a->n_obj, per_block), a->E);
+        if (smem <= 200 * 1024) {
+            R2S_CUDA_TRY(cudaFuncSetAttribute(lbs_blend_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            lbs_blend_kernel<true><<<grid, 512, smem, st>>>(*a, per_block);
+        } else {
+            lbs_blend_kernel<false><<<grid, 512, 0, st>>>(*a, per_block);
+        }
         R2S_LAUNCH_CHECK();
     }
     return R2S_OK;

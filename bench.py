@@ -334,7 +334,7 @@ def run_ours(args):
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
         "metrics_allgather": {"per_rank": gathered, "fields": ["steps", "seconds", "checksum_x", "checksum_rgb"]},
     }
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # timed on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(args, env)
     if world > 1:
         import torch.distributed as dist

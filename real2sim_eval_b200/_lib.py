@@ -22,7 +22,7 @@ class PhysDesc(C.Structure):  # include/r2s_phys.h: r2s_phys_desc
     _fields_ = [
         ("E", c_i32), ("N", c_i32), ("S", c_i32), ("n_substeps", c_i32), ("self_collision", c_i32),
         ("reverse_z", c_i32), ("use_pusher", c_i32), ("sign_mode", c_i32), ("coll_row_cap", c_i32),
-        ("threads", c_i32), ("precise", c_i32),
+        ("threads", c_i32), ("precise", c_i32), ("mesh_accel", c_i32), ("pad0_", c_i32),
         ("dt", c_f), ("dashpot_damping", c_f), ("drag_damping", c_f),
         ("spring_Y_min", c_f), ("spring_Y_max", c_f), ("collision_dist", c_f),
         ("collide_elas", c_f), ("collide_fric", c_f), ("collide_eef_elas", c_f), ("collide_eef_fric", c_f),

@@ -83,6 +83,17 @@ struct FrameParams {
     const float* dyn_omega;  // [(E)][3]
     long long omega_stride;
     float* coll_forces;  // [E][F][3]
+    // rigid dynamic mesh accelerator (set when the whole mesh is one rigidly moving tool, e.g. the pusher)
+    int accel;                  // 0: brute force over the faces; 1: uniform grid + pseudonormal sign
+    const float* frec;          // [F][24] rest-frame face record: v0 v1 v2 | n | e01 e12 e20 | pad
+    const float* vnorm;         // [V][3] angle-weighted vertex pseudonormals
+    const int* cell_start;      // [ncell + 1]
+    const int* cell_tris;       // triangle ids per cell
+    float gx0, gy0, gz0, gh;    // grid origin, cell edge
+    int gnx, gny, gnz;
+    int a0, a1, a2;             // anchor vertices (non-collinear) that define the rigid frame
+    float rest_frame[12];       // rest basis f1 f2 f3 (rows) and rest anchor r0
+    float rest_box[6];          // rest-pose bounding box lo / hi
 };
 
 // ------------------------------------------------------------------ mesh query
@@ -129,6 +140,119 @@ __device__ __forceinline__ void closest_bary(float3 a, float3 b, float3 c, float
     float denom = 1.0f / (va + vb + vc);
     float vv = vb * denom, ww = vc * denom;
     u = 1.0f - vv - ww; v = vv;
+}
+
+// As closest_bary, also reporting the Voronoi region of the closest point:
+// 0 face interior, 1/2/3 vertex a/b/c, 4 edge ab, 5 edge ac, 6 edge bc.
+__device__ __forceinline__ int closest_bary_region(float3 a, float3 b, float3 c, float3 p, float& u, float& v)
+{
+    float3 ab = b - a, ac = c - a, ap = p - a;
+    float d1 = dot3(ab, ap), d2 = dot3(ac, ap);
+    if (d1 <= 0.0f && d2 <= 0.0f) { u = 1.0f; v = 0.0f; return 1; }
+    float3 bp = p - b;
+    float d3 = dot3(ab, bp), d4 = dot3(ac, bp);
+    if (d3 >= 0.0f && d4 <= d3) { u = 0.0f; v = 1.0f; return 2; }
+    float vc = d1 * d4 - d3 * d2;
+    if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) {
+        float t = d1 / (d1 - d3);
+        u = 1.0f - t; v = t; return 4;
+    }
+    float3 cp = p - c;
+    float d5 = dot3(ab, cp), d6 = dot3(ac, cp);
+    if (d6 >= 0.0f && d5 <= d6) { u = 0.0f; v = 0.0f; return 3; }
+    float vb = d5 * d2 - d1 * d6;
+    if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) {
+        float w = d2 / (d2 - d6);
+        u = 1.0f - w; v = 0.0f; return 5;
+    }
+    float va = d3 * d6 - d5 * d4;
+    if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) {
+        float w = (d4 - d3) / ((d4 - d3) + (d5 - d6));
+        u = 0.0f; v = 1.0f - w; return 6;
+    }
+    float denom = 1.0f / (va + vb + vc);
+    float vv = vb * denom, ww = vc * denom;
+    u = 1.0f - vv - ww; v = vv;
+    return 0;
+}
+
+// Closest point of a RIGID mesh through a uniform grid built once in its rest frame (one warp per query,
+// p already transformed into the rest frame).  Shells of cells around p's cell are visited in growing
+// Chebyshev radius r; every triangle closer than r*h has been seen after shell r, so the search stops when the
+// best distance is <= r*h (or r*h exceeds max_dist).  Same result as the brute-force scan: strictly smaller
+// squared distance from max_dist^2, ties to the lower face index.  The sign is the angle-weighted pseudonormal
+// test at the closest feature (Baerentzen & Aanaes): for a closed mesh it is the inside/outside the winding
+// number > 0.6 test yields, without a sum over all faces.  Returns the closest point in the rest frame.
+struct GridView {  // the fields of FrameParams the grid query needs, passed by value (kernel parameters live in
+                   // the constant bank; taking a reference to the whole struct would copy it to local memory)
+    const float* frec; const float* vnorm; const int* cell_start; const int* cell_tris; const int* faces;
+    float gx0, gy0, gz0, gh;
+    int gnx, gny, gnz, sign_mode;
+};
+
+__device__ __noinline__ bool mesh_query_grid(const GridView p, float3 q, float max_dist, int& face, float3& c_rest,
+                                             float& sign)
+{
+    const unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const float inv_h = 1.0f / p.gh;
+    const int cx = (int)floorf((q.x - p.gx0) * inv_h), cy = (int)floorf((q.y - p.gy0) * inv_h),
+              cz = (int)floorf((q.z - p.gz0) * inv_h);
+    if (cx < 0 || cy < 0 || cz < 0 || cx >= p.gnx || cy >= p.gny || cz >= p.gnz) return false;  // farther than max_dist
+    float best = max_dist * max_dist;
+    int hit = 0x7fffffff, region = 0;
+    float bu = 0.f, bv = 0.f;
+    const int r_max = (int)ceilf(max_dist * inv_h) + 1;
+    for (int r = 0; r <= r_max; ++r) {
+        const int w = 2 * r + 1, n_cells = w * w * w;
+        for (int k = lane; k < n_cells; k += 32) {
+            const int dz = k / (w * w) - r, dy = (k / w) % w - r, dx = k % w - r;
+            if (max(max(abs(dx), abs(dy)), abs(dz)) != r) continue;  // interior cells were visited by earlier shells
+            const int x = cx + dx, y = cy + dy, z = cz + dz;
+            if (x < 0 || y < 0 || z < 0 || x >= p.gnx || y >= p.gny || z >= p.gnz) continue;
+            const int cell = (z * p.gny + y) * p.gnx + x;
+            for (int t = p.cell_start[cell]; t < p.cell_start[cell + 1]; ++t) {
+                const int fc = p.cell_tris[t];
+                const float* fr = p.frec + (size_t)fc * 24;
+                const float3 a = f3(fr[0], fr[1], fr[2]), b = f3(fr[3], fr[4], fr[5]), c = f3(fr[6], fr[7], fr[8]);
+                float uu, vv;
+                const int reg = closest_bary_region(a, b, c, q, uu, vv);
+                const float3 cp = a * uu + b * vv + c * (1.0f - uu - vv);
+                const float3 d = cp - q;
+                const float d2 = dot3(d, d);
+                if (d2 < best || (d2 == best && fc < hit)) { best = d2; hit = fc; bu = uu; bv = vv; region = reg; }
+            }
+        }
+        float wb = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wb = fminf(wb, __shfl_xor_sync(kFull, wb, o));
+        const float reach = (float)r * p.gh;
+        if (wb <= reach * reach || reach > max_dist) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(kFull, best, o);
+        const int oh = __shfl_xor_sync(kFull, hit, o);
+        const float ou = __shfl_xor_sync(kFull, bu, o), ov = __shfl_xor_sync(kFull, bv, o);
+        const int oreg = __shfl_xor_sync(kFull, region, o);
+        if (ob < best || (ob == best && oh < hit)) { best = ob; hit = oh; bu = ou; bv = ov; region = oreg; }
+    }
+    if (hit == 0x7fffffff) return false;
+    face = hit;
+    const float* fr = p.frec + (size_t)hit * 24;
+    const float3 a = f3(fr[0], fr[1], fr[2]), b = f3(fr[3], fr[4], fr[5]), c = f3(fr[6], fr[7], fr[8]);
+    c_rest = a * bu + b * bv + c * (1.0f - bu - bv);
+    float3 n;
+    if (region == 0) n = f3(fr[9], fr[10], fr[11]);
+    else if (region == 4) n = f3(fr[12], fr[13], fr[14]);       // edge ab
+    else if (region == 6) n = f3(fr[15], fr[16], fr[17]);       // edge bc
+    else if (region == 5) n = f3(fr[18], fr[19], fr[20]);       // edge ca
+    else {
+        const int vid = p.faces[3 * hit + (region - 1)];
+        n = f3(p.vnorm[3 * vid], p.vnorm[3 * vid + 1], p.vnorm[3 * vid + 2]);
+    }
+    sign = (p.sign_mode == 1 || dot3(q - c_rest, n) >= 0.0f) ? 1.0f : -1.0f;
+    return true;
 }
 
 __device__ __forceinline__ float solid_angle(float3 a, float3 b, float3 c, float3 p)
@@ -198,7 +322,7 @@ __device__ __forceinline__ float3 mesh_eval(const MeshView& m, int face, float u
 // kPrecise: IEEE sqrt / divisions in the reference's expression order (SMW:87-99).
 // !kPrecise: one rsqrt + Newton step gives 1/len, the rest length is stored as its reciprocal;
 // same formula, ~4x fewer instructions per spring, results within a few ulp of the precise path.
-template <int G, bool kSmemState, bool kPrecise>
+template <int G, bool kSmemState, bool kPrecise, bool kAccel>
 __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
 {
     extern __shared__ float4 smem4[];
@@ -217,6 +341,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         (kSmemState ? sizeof(float4) * 2 * N + sizeof(float) * 3 * Npad : 0);
     float* s_aabb = reinterpret_cast<float*>(sp); sp += sizeof(float) * 16;  // [0..5] dyn, [6..11] static
     int* s_ncand = reinterpret_cast<int*>(s_aabb + 12);                      // candidates of this substep
+    float* s_rigid = reinterpret_cast<float*>(sp); sp += sizeof(float) * 16; // world = R rest + t of this substep (accel)
     int* s_cand = reinterpret_cast<int*>(sp);                                // particles near the mesh
     if (p.F > 0) sp += sizeof(int) * ((N + 3) & ~3);
     float* s_dyn = reinterpret_cast<float*>(sp);
@@ -258,6 +383,10 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
     const float* g_omega = has_mesh ? p.dyn_omega + (size_t)e * p.omega_stride : nullptr;
     float* g_forces = has_mesh ? p.coll_forces + (size_t)e * p.F * 3 : nullptr;
     float* forces = p.smem_forces ? s_forces : g_forces;
+    // collision_forces is zeroed before every substep (SMW:900), so only the LAST substep's contacts are ever
+    // visible: clear once here and accumulate only in that substep
+    if (has_mesh)
+        for (int k = tid; k < 3 * p.F; k += nthreads) forces[k] = 0.0f;
     __syncthreads();
 
     constexpr unsigned kFull = 0xffffffffu;
@@ -270,7 +399,40 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
         // ============ phase A prologue: mesh vertices of this substep, force clear
         if (has_mesh) {
             const float* row = g_interp + (size_t)step * p.n_dyn * 3;
-            if (tid < 32) {  // SMW:889-899 set_mesh_points + refit (bounds)
+            if (kAccel) {
+                // rigid tool: fit world = R rest + t from three anchor vertices of this substep's row, and take
+                // the bounding box of the transformed rest box (no per-vertex pass, no refit)
+                if (tid == 0) {
+                    const float3 c0 = f3(row[3 * p.a0], row[3 * p.a0 + 1], row[3 * p.a0 + 2]);
+                    const float3 c1 = f3(row[3 * p.a1], row[3 * p.a1 + 1], row[3 * p.a1 + 2]);
+                    const float3 c2 = f3(row[3 * p.a2], row[3 * p.a2 + 1], row[3 * p.a2 + 2]);
+                    const float3 e1 = normalize3(c1 - c0);
+                    const float3 e3 = normalize3(cross3(c1 - c0, c2 - c0));
+                    const float3 e2 = cross3(e3, e1);
+                    const float* f = p.rest_frame;  // rows f1, f2, f3, then r0
+                    float R[9];
+                    for (int r = 0; r < 3; ++r) {
+                        const float er[3] = {r == 0 ? e1.x : (r == 1 ? e1.y : e1.z), r == 0 ? e2.x : (r == 1 ? e2.y : e2.z),
+                                             r == 0 ? e3.x : (r == 1 ? e3.y : e3.z)};
+                        for (int c = 0; c < 3; ++c) R[3 * r + c] = er[0] * f[c] + er[1] * f[3 + c] + er[2] * f[6 + c];
+                    }
+                    const float3 r0 = f3(f[9], f[10], f[11]);
+                    const float3 t = c0 - f3(R[0] * r0.x + R[1] * r0.y + R[2] * r0.z, R[3] * r0.x + R[4] * r0.y + R[5] * r0.z,
+                                             R[6] * r0.x + R[7] * r0.y + R[8] * r0.z);
+                    for (int k = 0; k < 9; ++k) s_rigid[k] = R[k];
+                    s_rigid[9] = t.x; s_rigid[10] = t.y; s_rigid[11] = t.z;
+                    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+                    for (int corner = 0; corner < 8; ++corner) {
+                        const float bx = p.rest_box[(corner & 1) ? 3 : 0], by = p.rest_box[(corner & 2) ? 4 : 1],
+                                    bz = p.rest_box[(corner & 4) ? 5 : 2];
+                        const float w[3] = {R[0] * bx + R[1] * by + R[2] * bz + t.x, R[3] * bx + R[4] * by + R[5] * bz + t.y,
+                                            R[6] * bx + R[7] * by + R[8] * bz + t.z};
+                        for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], w[c]); hi[c] = fmaxf(hi[c], w[c]); }
+                    }
+                    for (int c = 0; c < 3; ++c) { s_aabb[c] = lo[c]; s_aabb[3 + c] = hi[c]; }
+                    *s_ncand = 0;
+                }
+            } else if (tid < 32) {  // SMW:889-899 set_mesh_points + refit (bounds)
                 float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
                 for (int k = tid; k < p.n_dyn; k += 32)
                     for (int c = 0; c < 3; ++c) {
@@ -287,8 +449,6 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                     for (int c = 0; c < 3; ++c) { s_aabb[c] = lo[c]; s_aabb[3 + c] = hi[c]; }
                     *s_ncand = 0;
                 }
-            } else if (tid < 64) {  // SMW:900 collision_forces.zero_()
-                for (int k = tid - 32; k < 3 * p.F; k += 32) forces[k] = 0.0f;
             }
         }
         // ============ phase A: spring forces (gather) + velocity update -> svb
@@ -475,13 +635,32 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                 float3 v0 = xyz(sv[i]);
                 float3 next_x = x0 + v0 * dt;
                 float3 next_v = v0;
-                int face; float u, v, sign;
-                if (mesh_query_warp(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face, u, v, sign)) {
+                // closest point on the mesh within max_dist of `q` and the inside/outside sign there
+                auto query = [&](float3 q, int& qface, float3& qpc, float& qsign) -> bool {
+                    if (!kAccel) {
+                        float qu, qv;
+                        if (!mesh_query_warp(mesh, q, 0.02f, 0.6f, p.sign_mode, qface, qu, qv, qsign)) return false;
+                        qpc = mesh_eval(mesh, qface, qu, qv);
+                        return true;
+                    }
+                    const float* R = s_rigid;  // world = R rest + t  =>  rest = R^T (world - t)
+                    const float3 w = f3(q.x - R[9], q.y - R[10], q.z - R[11]);
+                    const float3 qr = f3(R[0] * w.x + R[3] * w.y + R[6] * w.z, R[1] * w.x + R[4] * w.y + R[7] * w.z,
+                                         R[2] * w.x + R[5] * w.y + R[8] * w.z);
+                    float3 cr;
+                    const GridView gv = {p.frec, p.vnorm, p.cell_start, p.cell_tris, p.faces, p.gx0, p.gy0, p.gz0, p.gh,
+                                         p.gnx, p.gny, p.gnz, p.sign_mode};
+                    if (!mesh_query_grid(gv, qr, 0.02f, qface, cr, qsign)) return false;
+                    qpc = f3(R[0] * cr.x + R[1] * cr.y + R[2] * cr.z + R[9], R[3] * cr.x + R[4] * cr.y + R[5] * cr.z + R[10],
+                             R[6] * cr.x + R[7] * cr.y + R[8] * cr.z + R[11]);
+                    return true;
+                };
+                int face; float sign; float3 pc;
+                if (query(next_x, face, pc, sign)) {
                     int is_gripper;
                     const int mm = p.mesh_map[face];
                     if (!p.use_pusher) is_gripper = (mm == 0) ? 1 : ((mm == 1) ? 2 : 0);
                     else is_gripper = (mm >= 0) ? 1 : 0;
-                    const float3 pc = mesh_eval(mesh, face, u, v);
                     const float3 delta = next_x - pc;
                     const float dist = len3(delta) * sign;
                     const float margin = (is_gripper >= 1 && !p.use_pusher) ? 0.005f : 0.001f;
@@ -511,9 +690,8 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         if (is_gripper >= 1) next_v = next_v + real_dyn;
                         if (is_gripper >= 1) {
                             next_x = x0 + next_v * dt;
-                            int face2; float u2, v2, sign2;
-                            if (mesh_query_warp(mesh, next_x, 0.02f, 0.6f, p.sign_mode, face2, u2, v2, sign2)) {
-                                const float3 p2 = mesh_eval(mesh, face2, u2, v2);
+                            int face2; float sign2; float3 p2;
+                            if (query(next_x, face2, p2, sign2)) {
                                 const float3 delta2 = next_x - p2;
                                 const float err2 = len3(delta2) * sign2 - margin;
                                 if (err2 < 0.0f) {
@@ -524,7 +702,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         } else {
                             next_x = next_x - normal * err;
                         }
-                        if (lane == 0) {
+                        if (lane == 0 && step == p.n_sub - 1) {
                             const float3 dvn = (v_normal_new - v_normal) / dt;
                             const int fm = p.face_map[face];
                             atomicAdd(forces + 3 * fm, dvn.x);
@@ -759,6 +937,17 @@ struct r2s_phys {
     float* dyn_omega = nullptr;
     int motion_per_env = 0;
     int motion_substeps = 0;
+    // rigid-tool accelerator
+    int accel = 0;
+    float* frec = nullptr;
+    float* vnorm = nullptr;
+    int* cell_start = nullptr;
+    int* cell_tris = nullptr;
+    float grid0[3] = {0, 0, 0}, grid_h = 0.f;
+    int grid_n[3] = {0, 0, 0};
+    int anchors[3] = {0, 0, 0};
+    float rest_frame[12] = {0};
+    float rest_box[6] = {0};
     // launch config
     bool smem_state = true;
     size_t smem_bytes = 0;
@@ -780,14 +969,14 @@ int dmalloc(T** p, size_t n)
 int configure_launch(r2s_phys* h)
 {
     const int N = h->d.N;
-    size_t misc = sizeof(float) * 16;
+    size_t misc = sizeof(float) * 32;   // bounding boxes + rigid transform
     h->stage_dyn = 0;
     h->smem_forces = 0;
     if (h->F > 0) {
         size_t dynb = sizeof(float) * 3 * ((h->n_dyn + 3) & ~3);
         size_t fb = sizeof(float) * 3 * h->F;
         misc += sizeof(int) * ((N + 3) & ~3);  // queue of particles near the mesh
-        if (dynb <= 24 * 1024) { h->stage_dyn = 1; misc += dynb; }
+        if (dynb <= 24 * 1024 && !h->accel) { h->stage_dyn = 1; misc += dynb; }
         if (fb <= 24 * 1024) { h->smem_forces = 1; misc += fb; }
     }
     size_t state = sizeof(float4) * 2 * (size_t)N + sizeof(float) * 3 * ((N + 3) & ~3);
@@ -798,21 +987,161 @@ int configure_launch(r2s_phys* h)
     return R2S_OK;
 }
 
-template <int G, bool kSmem, bool kPrecise>
+// Rigid-tool accelerator (host, once per set_mesh): face / edge / vertex pseudonormals, three anchor vertices
+// that define the tool's frame, and a uniform grid of triangle lists over the rest pose grown by max_dist.
+int build_accel(r2s_phys* h, const float* verts, const int* faces, int V, int F)
+{
+    auto P = [&](int i) { return verts + 3 * (size_t)i; };
+    auto sub = [](const float* a, const float* b, double* o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; };
+    auto crs = [](const double* a, const double* b, double* o) {
+        o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    auto nrm = [](double* a) { double l = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]); if (l > 0) { a[0] /= l; a[1] /= l; a[2] /= l; } return l; };
+    std::vector<double> fn(3 * (size_t)F), vn(3 * (size_t)V, 0.0);
+    for (int f = 0; f < F; ++f) {
+        const int* t = faces + 3 * f;
+        double e1[3], e2[3], n[3];
+        sub(P(t[1]), P(t[0]), e1); sub(P(t[2]), P(t[0]), e2);
+        crs(e1, e2, n); nrm(n);
+        for (int c = 0; c < 3; ++c) fn[3 * (size_t)f + c] = n[c];
+        for (int k = 0; k < 3; ++k) {  // angle-weighted vertex pseudonormals
+            double a[3], b[3];
+            sub(P(t[(k + 1) % 3]), P(t[k]), a); sub(P(t[(k + 2) % 3]), P(t[k]), b);
+            nrm(a); nrm(b);
+            double cs = std::max(-1.0, std::min(1.0, a[0] * b[0] + a[1] * b[1] + a[2] * b[2]));
+            const double ang = acos(cs);
+            for (int c = 0; c < 3; ++c) vn[3 * (size_t)t[k] + c] += ang * n[c];
+        }
+    }
+    // edge -> adjacent faces
+    std::vector<std::pair<long long, int>> edges;
+    edges.reserve(3 * (size_t)F);
+    for (int f = 0; f < F; ++f)
+        for (int k = 0; k < 3; ++k) {
+            long long a = faces[3 * f + k], b = faces[3 * f + (k + 1) % 3];
+            edges.push_back({std::min(a, b) * (long long)V + std::max(a, b), f});
+        }
+    std::sort(edges.begin(), edges.end());
+    auto other_face = [&](int f, int a, int b) {
+        const long long key = (long long)std::min(a, b) * V + std::max(a, b);
+        auto it = std::lower_bound(edges.begin(), edges.end(), std::make_pair(key, -1));
+        for (; it != edges.end() && it->first == key; ++it)
+            if (it->second != f) return it->second;
+        return f;  // boundary edge of an open mesh
+    };
+    std::vector<float> frec(24 * (size_t)F, 0.f), vnf(3 * (size_t)V);
+    for (int i = 0; i < 3 * V; ++i) vnf[i] = (float)vn[i];
+    for (int f = 0; f < F; ++f) {
+        const int* t = faces + 3 * f;
+        float* r = frec.data() + 24 * (size_t)f;
+        for (int k = 0; k < 3; ++k)
+            for (int c = 0; c < 3; ++c) r[3 * k + c] = P(t[k])[c];
+        for (int c = 0; c < 3; ++c) r[9 + c] = (float)fn[3 * (size_t)f + c];
+        const int pairs[3][2] = {{0, 1}, {1, 2}, {2, 0}};  // e01, e12, e20
+        for (int k = 0; k < 3; ++k) {
+            const int g = other_face(f, t[pairs[k][0]], t[pairs[k][1]]);
+            for (int c = 0; c < 3; ++c) r[12 + 3 * k + c] = (float)(fn[3 * (size_t)f + c] + fn[3 * (size_t)g + c]);
+        }
+    }
+    // anchors: vertex 0, the vertex farthest from it, the vertex farthest from their line
+    int a0 = 0, a1 = 0, a2 = 0;
+    double best = -1;
+    for (int i = 0; i < V; ++i) {
+        double d[3]; sub(P(i), P(a0), d);
+        const double l = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+        if (l > best) { best = l; a1 = i; }
+    }
+    double ax[3]; sub(P(a1), P(a0), ax); nrm(ax);
+    best = -1;
+    for (int i = 0; i < V; ++i) {
+        double d[3], c[3]; sub(P(i), P(a0), d); crs(ax, d, c);
+        const double l = c[0] * c[0] + c[1] * c[1] + c[2] * c[2];
+        if (l > best) { best = l; a2 = i; }
+    }
+    if (best <= 1e-12) { r2s::set_error("r2s_phys_set_mesh: degenerate (collinear) mesh cannot be accelerated"); return R2S_ERR_INVALID; }
+    double d2[3], e3[3], e2[3];
+    sub(P(a2), P(a0), d2); crs(ax, d2, e3); nrm(e3); crs(e3, ax, e2);
+    for (int c = 0; c < 3; ++c) { h->rest_frame[c] = (float)ax[c]; h->rest_frame[3 + c] = (float)e2[c]; h->rest_frame[6 + c] = (float)e3[c];
+                                  h->rest_frame[9 + c] = P(a0)[c]; }
+    h->anchors[0] = a0; h->anchors[1] = a1; h->anchors[2] = a2;
+    // grid over the rest box grown by max_dist + one cell
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int i = 0; i < V; ++i)
+        for (int c = 0; c < 3; ++c) { lo[c] = std::min(lo[c], P(i)[c]); hi[c] = std::max(hi[c], P(i)[c]); }
+    for (int c = 0; c < 3; ++c) { h->rest_box[c] = lo[c]; h->rest_box[3 + c] = hi[c]; }
+    float cell = 0.004f;
+    long long ncell = 0;
+    for (;;) {
+        ncell = 1;
+        for (int c = 0; c < 3; ++c) {
+            h->grid0[c] = lo[c] - (0.02f + cell);
+            h->grid_n[c] = (int)ceilf((hi[c] - lo[c] + 2.f * (0.02f + cell)) / cell) + 1;
+            ncell *= h->grid_n[c];
+        }
+        if (ncell <= (1ll << 22)) break;
+        cell *= 1.5f;
+    }
+    h->grid_h = cell;
+    std::vector<int> start(ncell + 1, 0);
+    auto cell_range = [&](int f, int* c0, int* c1) {
+        const int* t = faces + 3 * f;
+        for (int c = 0; c < 3; ++c) {
+            const float mn = std::min(P(t[0])[c], std::min(P(t[1])[c], P(t[2])[c]));
+            const float mx = std::max(P(t[0])[c], std::max(P(t[1])[c], P(t[2])[c]));
+            c0[c] = std::max(0, (int)floorf((mn - h->grid0[c]) / cell));
+            c1[c] = std::min(h->grid_n[c] - 1, (int)floorf((mx - h->grid0[c]) / cell));
+        }
+    };
+    for (int pass = 0; pass < 2; ++pass) {
+        std::vector<int> cur;
+        std::vector<int> tris;
+        if (pass == 1) {
+            for (long long i = 0; i < ncell; ++i) start[i + 1] += start[i];
+            cur.assign(start.begin(), start.end() - 1);
+            tris.resize(start[ncell]);
+        }
+        for (int f = 0; f < F; ++f) {
+            int c0[3], c1[3];
+            cell_range(f, c0, c1);
+            for (int z = c0[2]; z <= c1[2]; ++z)
+                for (int y = c0[1]; y <= c1[1]; ++y)
+                    for (int x = c0[0]; x <= c1[0]; ++x) {
+                        const long long id = ((long long)z * h->grid_n[1] + y) * h->grid_n[0] + x;
+                        if (pass == 0) start[id + 1]++;
+                        else tris[cur[id]++] = f;
+                    }
+        }
+        if (pass == 1) {
+            if (dmalloc(&h->frec, frec.size()) || dmalloc(&h->vnorm, vnf.size()) || dmalloc(&h->cell_start, start.size()) ||
+                dmalloc(&h->cell_tris, tris.size()))
+                return R2S_ERR_CUDA;
+            R2S_CUDA_TRY(cudaMemcpy(h->frec, frec.data(), sizeof(float) * frec.size(), cudaMemcpyHostToDevice));
+            R2S_CUDA_TRY(cudaMemcpy(h->vnorm, vnf.data(), sizeof(float) * vnf.size(), cudaMemcpyHostToDevice));
+            R2S_CUDA_TRY(cudaMemcpy(h->cell_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
+            if (!tris.empty())
+                R2S_CUDA_TRY(cudaMemcpy(h->cell_tris, tris.data(), sizeof(int) * tris.size(), cudaMemcpyHostToDevice));
+        }
+    }
+    h->accel = 1;
+    return R2S_OK;
+}
+
+template <int G, bool kSmem, bool kPrecise, bool kAccel>
 int launch_frame_t(r2s_phys* h, const FrameParams& fp, cudaStream_t st)
 {
-    R2S_CUDA_TRY(cudaFuncSetAttribute(frame_kernel<G, kSmem, kPrecise>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)h->smem_bytes));
-    frame_kernel<G, kSmem, kPrecise><<<h->d.E, h->threads, h->smem_bytes, st>>>(fp);
+    R2S_CUDA_TRY(cudaFuncSetAttribute(frame_kernel<G, kSmem, kPrecise, kAccel>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+    frame_kernel<G, kSmem, kPrecise, kAccel><<<h->d.E, h->threads, h->smem_bytes, st>>>(fp);
     R2S_LAUNCH_CHECK();
     return R2S_OK;
 }
 
-template <int G>
+template <int G, bool kAccel>
 int launch_frame(r2s_phys* h, const FrameParams& fp, cudaStream_t st)
 {
-    if (h->smem_state) return h->d.precise ? launch_frame_t<G, true, true>(h, fp, st) : launch_frame_t<G, true, false>(h, fp, st);
-    return h->d.precise ? launch_frame_t<G, false, true>(h, fp, st) : launch_frame_t<G, false, false>(h, fp, st);
+    if (h->smem_state)
+        return h->d.precise ? launch_frame_t<G, true, true, kAccel>(h, fp, st) : launch_frame_t<G, true, false, kAccel>(h, fp, st);
+    return h->d.precise ? launch_frame_t<G, false, true, kAccel>(h, fp, st) : launch_frame_t<G, false, false, kAccel>(h, fp, st);
 }
 
 }  // namespace
@@ -916,7 +1245,7 @@ int r2s_phys_destroy(r2s_phys* h)
     void* ptrs[] = {h->row_ptr, h->nbr, h->sid, h->nbr_k, h->rest_csr, h->logY, h->mass, h->mask, h->x4, h->v4,
                     h->vb_scratch, h->coll_num, h->coll_idx, h->status, h->resting, h->key_scratch,
                     h->stat_verts, h->faces, h->mesh_map, h->face_map, h->coll_forces, h->interp_pts,
-                    h->interp_center, h->dyn_vel, h->dyn_omega};
+                    h->interp_center, h->dyn_vel, h->dyn_omega, h->frec, h->vnorm, h->cell_start, h->cell_tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -1004,6 +1333,9 @@ int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, con
     for (void* p : old)
         if (p) cudaFree(p);
     h->interp_pts = h->interp_center = h->dyn_vel = h->dyn_omega = nullptr;
+    for (void* q : {(void*)h->frec, (void*)h->vnorm, (void*)h->cell_start, (void*)h->cell_tris})
+        if (q) cudaFree(q);
+    h->frec = h->vnorm = nullptr; h->cell_start = h->cell_tris = nullptr; h->accel = 0;
     h->V = V; h->F = F; h->n_dyn = n_dyn;
     const int E = h->d.E, ns = h->d.n_substeps;
     if (dmalloc(&h->stat_verts, (size_t)3 * V) || dmalloc(&h->faces, (size_t)3 * F) || dmalloc(&h->mesh_map, F) ||
@@ -1032,6 +1364,12 @@ int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, con
     R2S_CUDA_TRY(cudaMemcpy(h->dyn_omega, zero.data(), sizeof(float) * 3, cudaMemcpyHostToDevice));
     h->motion_per_env = 0;
     h->motion_substeps = ns;
+    // a mesh that is entirely one rigidly moving tool (the pusher: every vertex dynamic) gets the grid accelerator
+    const int want = h->d.mesh_accel;
+    if (want > 0 || (want == 0 && h->d.use_pusher && n_dyn == V && F >= 256)) {
+        R2S_REQUIRE(n_dyn == V, "r2s_phys_set_mesh: mesh_accel needs a fully dynamic (rigid tool) mesh");
+        if (int rc = build_accel(h, verts, faces, V, F)) return rc;
+    }
     return configure_launch(h);
 }
 
@@ -1120,12 +1458,20 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     p.dynvel_stride = pe * 6;
     p.omega_stride = pe * 3;
     p.coll_forces = h->coll_forces;
+    p.accel = h->accel;
+    p.frec = h->frec; p.vnorm = h->vnorm; p.cell_start = h->cell_start; p.cell_tris = h->cell_tris;
+    p.gx0 = h->grid0[0]; p.gy0 = h->grid0[1]; p.gz0 = h->grid0[2]; p.gh = h->grid_h;
+    p.gnx = h->grid_n[0]; p.gny = h->grid_n[1]; p.gnz = h->grid_n[2];
+    p.a0 = h->anchors[0]; p.a1 = h->anchors[1]; p.a2 = h->anchors[2];
+    for (int k = 0; k < 12; ++k) p.rest_frame[k] = h->rest_frame[k];
+    for (int k = 0; k < 6; ++k) p.rest_box[k] = h->rest_box[k];
     // lanes per adjacency row: 8 suits degrees ~30-60; R2S_PHYS_G overrides it for tuning
     static const int g_lanes = [] { const char* e = getenv("R2S_PHYS_G"); return e ? atoi(e) : 8; }();
-    if (g_lanes == 4) return launch_frame<4>(h, p, st);
-    if (g_lanes == 16) return launch_frame<16>(h, p, st);
-    if (g_lanes == 32) return launch_frame<32>(h, p, st);
-    return launch_frame<8>(h, p, st);
+    if (p.accel) return launch_frame<8, true>(h, p, st);
+    if (g_lanes == 4) return launch_frame<4, false>(h, p, st);
+    if (g_lanes == 16) return launch_frame<16, false>(h, p, st);
+    if (g_lanes == 32) return launch_frame<32, false>(h, p, st);
+    return launch_frame<8, false>(h, p, st);
 }
 
 int r2s_phys_get_ptrs(r2s_phys* h, r2s_phys_ptrs* out)

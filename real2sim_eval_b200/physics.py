@@ -80,7 +80,7 @@ class BatchedSpringMass:
                  spring_Y_max=1e5, collision_dist=0.005, self_collision=True, reverse_z=False,
                  collide_elas=0.5, collide_fric=0.3, collide_eef_elas=0.0, collide_eef_fric=1.0,
                  collide_self_elas=0.5, collide_self_fric=0.3, use_pusher=False, sign_mode=0, coll_row_cap=0,
-                 threads=0, precise=False, device="cuda"):
+                 threads=0, precise=False, mesh_accel=0, device="cuda"):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.R2SError("BatchedSpringMass needs a CUDA device: there is no CPU path")
@@ -102,6 +102,7 @@ class BatchedSpringMass:
         d.self_collision, d.reverse_z, d.use_pusher = int(bool(self_collision)), int(bool(reverse_z)), int(bool(use_pusher))
         d.sign_mode, d.coll_row_cap, d.threads = int(sign_mode), int(coll_row_cap), int(threads)
         d.precise = int(bool(precise))
+        d.mesh_accel = int(mesh_accel)
         d.dt, d.dashpot_damping, d.drag_damping = dt, dashpot_damping, drag_damping
         d.spring_Y_min, d.spring_Y_max, d.collision_dist = spring_Y_min, spring_Y_max, collision_dist
         d.collide_elas, d.collide_fric = collide_elas, collide_fric

@@ -200,6 +200,58 @@ def make_finger_mesh(length=0.045, half_w=0.011, half_t=0.004):
     return v.astype(np.float32), np.asarray(tris, dtype=np.int32)
 
 
+def make_rod_mesh(radius=0.0375, length=0.205, n_circ=24, n_len=16):
+    """Closed, outward-oriented triangulated cylinder along +z from z=0 (the shape of the shipped pusher,
+    assets/robots/xarm/.../pusher_20cm.stl: a 75 mm x 205 mm rod; n_circ=112, n_len=112 gives ~25k triangles)."""
+    ang = 2 * np.pi * np.arange(n_circ) / n_circ
+    ring = np.stack([radius * np.cos(ang), radius * np.sin(ang)], 1)
+    zs = np.linspace(0.0, length, n_len + 1)
+    verts = [np.concatenate([ring, np.full((n_circ, 1), z)], 1) for z in zs]
+    verts = np.concatenate(verts + [np.array([[0, 0, 0.0]]), np.array([[0, 0, length]])], 0)
+    ib, it = (n_len + 1) * n_circ, (n_len + 1) * n_circ + 1
+    tris = []
+    for k in range(n_len):
+        for i in range(n_circ):
+            j = (i + 1) % n_circ
+            a, b, c, d = k * n_circ + i, k * n_circ + j, (k + 1) * n_circ + j, (k + 1) * n_circ + i
+            tris += [(a, b, c), (a, c, d)]
+    for i in range(n_circ):
+        j = (i + 1) % n_circ
+        tris.append((ib, j, i))                                   # bottom cap, normal -z
+        tris.append((it, n_len * n_circ + i, n_len * n_circ + j))  # top cap, normal +z
+    return verts.astype(np.float32), np.asarray(tris, dtype=np.int32)
+
+
+def make_pusher(center, tilt=0.0, **kw) -> "Gripper":
+    """One rigid pusher rod hanging down with its tip at `center` (mesh_map 0 everywhere, use_pusher=True)."""
+    v, f = make_rod_mesh(**kw)
+    c, s = np.cos(tilt), np.sin(tilt)
+    R = np.array([[1, 0, 0], [0, c, -s], [0, s, c]])
+    v = (v.astype(np.float64) @ R.T + np.asarray(center, np.float64)).astype(np.float32)
+    return Gripper(v, f, np.zeros(len(f), np.int32), np.arange(len(f), dtype=np.int32))
+
+
+def rigid_motion_tables(g: "Gripper", n_substeps, dt, vel, omega=(0.0, 0.0, 0.0)):
+    """Per-substep tables of a RIGID tool (sim/physics/phystwin.py:462-510): rotation about the mesh centre with
+    angular velocity `omega` plus translation `vel`; returns interp_pts, interp_center, dyn_vel (1,3), dyn_omega (1,3)."""
+    vel, omega = np.asarray(vel, np.float64), np.asarray(omega, np.float64)
+    ctr0 = g.verts.astype(np.float64).mean(0)
+    pts, ctr = [], []
+    for s in range(1, n_substeps + 1):
+        t = s * dt
+        th = np.linalg.norm(omega) * t
+        if th > 0:
+            k = omega / np.linalg.norm(omega)
+            K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+            R = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+        else:
+            R = np.eye(3)
+        pts.append((g.verts.astype(np.float64) - ctr0) @ R.T + ctr0 + vel * t)
+        ctr.append(ctr0 + vel * t)
+    return (np.asarray(pts, np.float32), np.asarray(ctr, np.float32), (vel * 0.5)[None].astype(np.float32),
+            (-omega * 0.5)[None].astype(np.float32))
+
+
 @dataclass
 class Gripper:
     verts: np.ndarray      # (48,3) float32 at rest pose (left finger first)

@@ -271,3 +271,92 @@ def test_parameter_setters_and_reverse_z():
     o.step(); c.step()
     x, _ = _cmp(c, [o])
     assert (x[0][:, 2] < 1e-7).all(), "with reverse_z the ground is above: z stays <= 0"
+
+
+def test_static_mesh_and_gripper_together():
+    """Merged mesh = two dynamic fingers + one static obstacle (mesh_map -1, margin 1 mm, plain projection without
+    the re-query, world-frame contact, SMW:326-338, 344-347, 409-410)."""
+    sc = synth.make_rope(v_scale=0.0)
+    sc.v[:, 2] = -0.6                                            # the rope falls onto the obstacle
+    ns = 40
+    g = synth.make_gripper(center=(0.5, 0.0, 0.004), gap=0.022)
+    # static obstacle: a closed box (the finger prism scaled up) lying under the rope near x = 0.2
+    bv, bf = synth.make_finger_mesh(length=0.06, half_w=0.02, half_t=0.0045)
+    box = (bv[:, [2, 0, 1]] + np.array([0.17, 0.0, 0.0045], np.float32)).astype(np.float32)   # long axis along x
+    verts = np.concatenate([g.verts, box], 0)
+    faces = np.concatenate([g.faces, bf + len(g.verts)], 0)
+    mesh_map = np.concatenate([g.mesh_map, np.full(len(bf), -1)]).astype(np.int32)
+    face_map = np.arange(len(faces), dtype=np.int32)
+    mesh = dict(verts=verts, faces=faces, mesh_map=mesh_map, face_map=face_map, n_dyn_verts=len(g.verts))
+    tables = synth.gripper_motion(g, ns, sc.params["dt"], eef_vel=(0.0, 0.0, -0.2), close_speed=0.5)
+    o = _util.oracle_from_scene(sc, ns, mesh=mesh)
+    o.set_mesh_interactive(*tables)
+    c = _util.cuda_from_scenes([sc], ns)
+    c.set_mesh(**mesh)
+    c.set_mesh_motion(*tables)
+    o.update_collision_graph(); c.update_collision_graph()
+    o.step(); c.step()
+    o_free = _util.oracle_from_scene(sc, ns, mesh=_util.gripper_mesh_dict(g))   # same run without the obstacle
+    o_free.set_mesh_interactive(*tables)
+    o_free.update_collision_graph(); o_free.step()
+    near = (sc.x[:, 0] > 0.17) & (sc.x[:, 0] < 0.23)
+    assert np.abs(o.x[near] - o_free.x[near]).max() > 1e-4, "the static obstacle must deflect the rope"
+    _cmp(c, [o], tol_x=5e-6, tol_v=2e-2, outlier_frac=0.01, hard_x=2e-3)
+
+
+def _pusher_case(ns=40):
+    sc = synth.load_tblock()
+    g = synth.make_pusher(center=(0.32 - 0.0375 + 0.0006, 0.0, 0.004))          # rod surface 0.6 mm inside the T's -x face
+    tables = synth.rigid_motion_tables(g, ns, sc.params["dt"], vel=(0.4, 0.02, 0.0), omega=(0.0, 0.0, 1.5))
+    mesh = dict(verts=g.verts, faces=g.faces, mesh_map=g.mesh_map, face_map=g.face_map, n_dyn_verts=len(g.verts))
+    return sc, g, tables, mesh
+
+
+@pytest.mark.parametrize("mesh_accel", [-1, 1])
+def test_pusher_rigid_tool_brute_force_and_grid_accelerator(mesh_accel):
+    """use_pusher=True (SMW:334-338: every face >= 0 is the tool, margin 1 mm, eef friction): an 816-triangle rod pushes
+    the real T-block.  mesh_accel=-1 scans all faces with the exact winding number (as the oracle does); mesh_accel=1
+    searches a uniform grid in the rod's rest frame and takes the sign from the pseudonormal of the closest feature --
+    both must reproduce the oracle."""
+    ns = 40
+    sc, g, tables, mesh = _pusher_case(ns)
+    o = _util.oracle_from_scene(sc, ns, mesh=mesh, use_pusher=True, collide_eef_fric=0.2)
+    o.set_mesh_interactive(*tables)
+    c = _util.cuda_from_scenes([sc], ns, use_pusher=True, collide_eef_fric=0.2, mesh_accel=mesh_accel)
+    c.set_mesh(**mesh)
+    c.set_mesh_motion(*tables)
+    o.update_collision_graph(); c.update_collision_graph()
+    o.step(); c.step()
+    o_free = _util.oracle_from_scene(sc, ns)
+    o_free.step()
+    assert np.abs(o.x - o_free.x).max() > 1e-4, "the rod must push the block"
+    _cmp(c, [o], tol_x=5e-6, tol_v=2e-2, outlier_frac=0.01, hard_x=2e-3)
+
+
+def test_pusher_25k_triangles_runs_at_speed():
+    """The shipped pusher is 25,368 triangles; a synthetic rod of 25,312: the accelerated frame
+    must agree with the 816-triangle rod's physics to a geometric tolerance and finish quickly."""
+    import time
+    import torch
+    ns = 40
+    sc, g_small, tables_small, mesh_small = _pusher_case(ns)
+    v, f = synth.make_rod_mesh(n_circ=112, n_len=112)
+    g = synth.make_pusher(center=(0.32 - 0.0375 + 0.0006, 0.0, 0.004), n_circ=112, n_len=112)
+    assert len(g.faces) == 25312
+    tables = synth.rigid_motion_tables(g, ns, sc.params["dt"], vel=(0.4, 0.02, 0.0), omega=(0.0, 0.0, 1.5))
+    mesh = dict(verts=g.verts, faces=g.faces, mesh_map=g.mesh_map, face_map=g.face_map, n_dyn_verts=len(g.verts))
+    E = 32
+    c = _util.cuda_from_scenes([sc] * E, ns, per_env_rest=False, use_pusher=True, collide_eef_fric=0.2)
+    c.set_mesh(**mesh)
+    c.set_mesh_motion(*tables)
+    c.update_collision_graph()
+    c.step()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    c.step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    x, _ = c.get_state()
+    assert torch.equal(x[0].expand_as(x), x) and torch.isfinite(x).all()
+    assert dt < 0.5, f"{E} envs x {ns} substeps against 25k triangles took {dt:.3f} s"
+    print(f"pusher 25k tris: {E} envs x {ns} substeps in {dt * 1e3:.1f} ms")

@@ -749,6 +749,7 @@ struct GridParams {
     int* coll_idx;                  // [E][N][cap]
     int* status;                    // [E][4]
     unsigned long long* key_scratch;  // [E][npow2] when keys do not fit shared memory, else null
+    int stage_x;                      // positions staged in shared memory in cell-sorted order (after the keys)
 };
 
 // One CTA per environment: cell-sort the particles (bitonic on (cell, id) keys),
@@ -787,10 +788,16 @@ __global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
             __syncthreads();
         }
     unsigned* resting = p.resting + (size_t)e * p.resting_stride;
+    // positions in cell-sorted order next to the keys, so that walking a cell reads consecutive shared memory
+    float4* sxs = reinterpret_cast<float4*>(smem_raw + sizeof(unsigned long long) * (size_t)p.npow2);
+    if (p.stage_x) {
+        for (int t = tid; t < N; t += nt) sxs[t] = x4[(int)(keys[t] & 0xffffffffu)];
+        __syncthreads();
+    }
     int total = 0, overflow = 0;
     for (int t = tid; t < N; t += nt) {
         const int i = (int)(keys[t] & 0xffffffffu);  // wp.hash_grid_point_id: cell-sorted order
-        const float4 q = x4[i];
+        const float4 q = p.stage_x ? sxs[t] : x4[i];
         const float3 x1 = xyz(q);
         const float r = p.radius;
         const int xs = (int)((x1.x - r) * inv_w), ys = (int)((x1.y - r) * inv_w), zs = (int)((x1.z - r) * inv_w);
@@ -800,17 +807,21 @@ __global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
         const int mask1 = p.mask[i];
         int cnt = 0;
         int* row = kResting ? nullptr : p.coll_idx + ((size_t)e * N + i) * p.cap;
+        // cells are visited x fastest, then y, then z (Warp's hash_grid_query order); the cells of one x-run
+        // have consecutive ids unless the run wraps modulo 128, so one binary search serves the whole run
+        const bool x_wraps = ((xs + (1 << 20)) % R2S_GRID_DIM) > ((xe + (1 << 20)) % R2S_GRID_DIM) || xs + (1 << 20) < 0;
         for (int z = zs; z <= ze; ++z)
             for (int y = ys; y <= ye; ++y)
                 for (int xx = xs; xx <= xe; ++xx) {
                     const unsigned cell = (unsigned)grid_cell(xx, y, z);
+                    const unsigned cell_hi = x_wraps ? cell : (unsigned)grid_cell(xe, y, z);
                     const unsigned long long lo_key = (unsigned long long)cell << 32;
                     int lo = 0, hi = N;
                     while (lo < hi) {
                         const int mid = (lo + hi) >> 1;
                         if (keys[mid] < lo_key) lo = mid + 1; else hi = mid;
                     }
-                    for (; lo < N && (unsigned)(keys[lo] >> 32) == cell; ++lo) {
+                    for (; lo < N && (unsigned)(keys[lo] >> 32) <= cell_hi; ++lo) {
                         const int j = (int)(keys[lo] & 0xffffffffu);
                         if (kResting) {
                             if (j < i) {
@@ -818,18 +829,20 @@ __global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
                                 atomicOr(resting + (size_t)j * p.words + (i >> 5), 1u << (i & 31));
                             }
                         } else {
+                            // the three conditions of SMW:216-225 are a pure conjunction: the (cheap, usually
+                            // failing) distance test goes first, the resting-pair bits are fetched only for close pairs
                             if (j == i) continue;
+                            const float3 dis = xyz(p.stage_x ? sxs[lo] : x4[j]) - x1;
+                            const float dis_len = len3(dis);
+                            if (!(dis_len < p.coll_dist) || mask1 == p.mask[j]) continue;
                             const bool rest_ij = (resting[(size_t)i * p.words + (j >> 5)] >> (j & 31)) & 1u;
                             const bool rest_ji = (resting[(size_t)j * p.words + (i >> 5)] >> (i & 31)) & 1u;
                             if (rest_ij || rest_ji) continue;
-                            const float3 dis = xyz(x4[j]) - x1;
-                            const float dis_len = len3(dis);
-                            if (mask1 != p.mask[j] && dis_len < p.coll_dist) {
-                                if (cnt < p.cap) row[cnt++] = j;
-                                else overflow++;
-                            }
+                            if (cnt < p.cap) row[cnt++] = j;
+                            else overflow++;
                         }
                     }
+                    if (!x_wraps) break;  // the whole x-run was walked
                 }
         if (!kResting) { p.coll_num[(size_t)e * N + i] = cnt; total += cnt; }
     }
@@ -1412,7 +1425,12 @@ static int run_grid(r2s_phys* h, bool resting, cudaStream_t st)
     g.coll_dist = h->d.collision_dist;
     g.x4 = h->x4; g.mask = h->mask; g.resting = h->resting; g.resting_stride = (long long)h->d.N * h->words;
     g.coll_num = h->coll_num; g.coll_idx = h->coll_idx; g.status = h->status; g.key_scratch = h->key_scratch;
-    const size_t smem = h->key_scratch ? 0 : sizeof(unsigned long long) * (size_t)h->npow2;
+    size_t smem = h->key_scratch ? 0 : sizeof(unsigned long long) * (size_t)h->npow2;
+    g.stage_x = 0;
+    if (!h->key_scratch && smem + sizeof(float4) * (size_t)h->d.N + 1024 <= (size_t)h->max_smem_optin) {
+        g.stage_x = 1;
+        smem += sizeof(float4) * (size_t)h->d.N;
+    }
     if (resting) {
         R2S_CUDA_TRY(cudaMemsetAsync(h->resting, 0, sizeof(unsigned) * (size_t)h->d.E * h->d.N * h->words, st));
         R2S_CUDA_TRY(cudaFuncSetAttribute(grid_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -155,7 +155,7 @@ class BatchedEnv:
         return pts, ctr, dyn_vel, dyn_omega
 
     def step(self, motion=None, out=None):
-        """One frame for every env: [gripper tables ->] collision graph -> substeps -> skin -> render.
+        """One frame for every env: [gripper tables ->] collision graph -> substeps -> LBS -> render.
         `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None.
         `out`: optional (color, depth) device tensors to render into (double buffering)."""
         color, depth = out if out is not None else (self.color, self.depth)

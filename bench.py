@@ -363,6 +363,7 @@ def cpu_baseline(args, env=None):
     from concurrent.futures import ThreadPoolExecutor
 
     cores = os.cpu_count() or 1
+    physics_ref.set_threads(cores)
     n = args.cpu_sample_envs or min(cores, 32)
     W, H = args.res
     scene = {"rope": synth.make_rope, "sloth": synth.make_sloth, "tblock": synth.load_tblock}[args.scene]()
@@ -414,6 +415,7 @@ def run_reference(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     cores = os.cpu_count() or 1
+    omp_threads = physics_ref.set_threads(cores)     # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores
     n = args.ref_envs or min(cores, 64)
     W, H = args.res
     P = args.gaussians
@@ -488,7 +490,7 @@ def run_reference(args):
                          "sample": f"{n} envs per step: physics = oracle/physics_ref.c (CPU restatement of the Warp "
                                    f"kernels; warp-lang not installable) on {cores} host threads, render = unmodified "
                                    f"reference CUDA rasterizer (oracle/_ref) once per env with its blocking read-back",
-                         "physics_s_per_step": round(t_phys, 4)},
+                         "physics_s_per_step": round(t_phys, 4), "omp_threads": omp_threads},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
 

@@ -575,5 +575,15 @@ void oracle_phys_step_batch(oracle_phys *envs, int E, const oracle_csr *csr)
     for (int e = 0; e < E; ++e) oracle_phys_step(&envs[e], csr);
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the baseline legs of bench.py ask for the host's cores explicitly. */
+#ifdef _OPENMP
+#include <omp.h>
+void oracle_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+int oracle_get_max_threads(void) { return omp_get_max_threads(); }
+#else
+void oracle_set_threads(int n) { (void)n; }
+int oracle_get_max_threads(void) { return 1; }
+#endif
+
 int oracle_phys_struct_size(void) { return (int)sizeof(oracle_phys); }
 int oracle_phys_coll_cap(void) { return COLL_CAP; }

@@ -162,6 +162,12 @@ class SpringMassOracle:
         lib().oracle_phys_step(C.byref(self.s), C.byref(self.csr) if self.csr is not None else None)
 
 
+def set_threads(n: int) -> int:
+    """Use n OpenMP threads for step_batch (torchrun exports OMP_NUM_THREADS=1); returns the active maximum."""
+    lib().oracle_set_threads(int(n))
+    return int(lib().oracle_get_max_threads())
+
+
 def step_batch(envs: list[SpringMassOracle]):
     """Step E environments with one OpenMP thread each (cpu baseline)."""
     arr = (_Phys * len(envs))(*[e.s for e in envs])

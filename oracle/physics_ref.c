@@ -441,12 +441,24 @@ static void set_mesh_points(oracle_phys *s, int step)
 static void mesh_collision(oracle_phys *s, int step)
 {
     const float dt = s->dt;
+    /* bounding box of the mesh grown by max_dist: a point outside it has every triangle farther than
+     * max_dist, so its query cannot hit (what Warp's BVH traversal prunes; the result is unchanged) */
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int k = 0; k < s->n_verts; ++k)
+        for (int c = 0; c < 3; ++c) {
+            float q = s->mesh_pts[3 * k + c];
+            if (q < lo[c]) lo[c] = q;
+            if (q > hi[c]) hi[c] = q;
+        }
+    const float grow = 0.02f * 1.0001f + 1e-6f;
     for (int i = 0; i < s->N; ++i) {
         v3 x0 = ld(s->x, i), v0 = ld(s->v_bg, i);
         v3 next_x = add(x0, muls(v0, dt));
         v3 next_v = v0;
         int face; float u, v, sign;
-        if (mesh_query(s, next_x, 0.02f, 0.6f, &face, &u, &v, &sign)) {
+        int near_box = next_x.x >= lo[0] - grow && next_x.x <= hi[0] + grow && next_x.y >= lo[1] - grow &&
+                       next_x.y <= hi[1] + grow && next_x.z >= lo[2] - grow && next_x.z <= hi[2] + grow;
+        if (near_box && mesh_query(s, next_x, 0.02f, 0.6f, &face, &u, &v, &sign)) {
             int is_gripper;
             if (!s->use_pusher) {
                 if (s->mesh_map[face] == 0) is_gripper = 1;

@@ -147,7 +147,7 @@ def run_ours(args):
     env = BatchedEnv(cfg, dev)
     lib = _lib.load()
     E, ns = cfg.E, cfg.n_substeps
-    n_frames = args.warmup + args.steps + (0 if args.no_e2e else args.warmup + args.steps) + 2
+    n_frames = args.warmup + args.steps + (0 if args.no_e2e else 2 * (args.warmup + args.steps)) + 2
     acts = [env.make_actions(f) for f in range(n_frames)]           # host numpy, made before any timing
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     acts_pinned = [tuple(pin(a) for a in act) for act in acts]
@@ -220,69 +220,96 @@ def run_ours(args):
     value = world * E * args.steps / (ms_max / 1e3)
 
     # ---- end-to-end loop: host buffers in, host buffers out, copies inside the timed region.
-    # Device->host copies of step k (1.09 GB of RGB-D + particle state) run on a side stream while
-    # step k+1 computes into the other output buffer (double buffering); every byte is still moved
-    # and waited for inside the timed region.
-    e2e = None
+    # Device->host copies of step k (observations + particle state) run on a side stream while step k+1
+    # computes into the other output buffer (double buffering); every byte is still moved and waited for
+    # inside the timed region.  Observation format: "u8" = RGB as [B,H,W,3] uint8 (what the reference's
+    # evaluation loop holds on the host, experiments/eval_policy.py:248) + float32 depth; "f32" = the
+    # float32 CHW colour image + depth (the device-side tensors, 16 B/pixel).  The headline `e2e` is "u8";
+    # the float variant is reported next to it.
+    e2e = e2e_f32 = None
     if not args.no_e2e:
         N = env.base.N
-        hostbuf = [dict(x=torch.empty((E, N, 3)).pin_memory(), v=torch.empty((E, N, 3)).pin_memory(),
-                        color=torch.empty(env.color.shape).pin_memory(), depth=torch.empty(env.depth.shape).pin_memory())
-                   for _ in range(2)]
-        devbuf = [(env.color, env.depth), (torch.empty_like(env.color), torch.empty_like(env.depth))]
-        devstate = [(torch.empty((E, N, 3), device=dev), torch.empty((E, N, 3), device=dev)) for _ in range(2)]
-        h2d = sum(t.numel() * 4 for t in acts_pinned[0]) + (env.view_h.numel() + env.proj_h.numel() + env.campos_h.numel()) * 4
-        d2h = sum(t.numel() * 4 for t in hostbuf[0].values())
+        import ctypes
         main = torch.cuda.current_stream(dev)
         cs = torch.cuda.Stream(dev)
-        computed = [torch.cuda.Event() for _ in range(2)]
-        copied = [torch.cuda.Event() for _ in range(2)]
-        for ev in copied:
-            ev.record(cs)
         phys_lib = env.phys.lib
-        import ctypes
+        h2d = sum(t.numel() * 4 for t in acts_pinned[0]) + (env.view_h.numel() + env.proj_h.numel() + env.campos_h.numel()) * 4
 
-        def e2e_step(i, slot):
-            m = upload(i)                                    # H2D: gripper tables (pinned -> device)
-            env.view.copy_(env.view_h, non_blocking=True)    # H2D: cameras
-            env.proj.copy_(env.proj_h, non_blocking=True)
-            env.campos.copy_(env.campos_h, non_blocking=True)
-            main.wait_event(copied[slot])                    # the buffers of step i-2 have left the device
-            env.step(m, out=devbuf[slot])
-            xs, vs = devstate[slot]
-            _lib.check(phys_lib.r2s_phys_get_state(env.phys.h, ctypes.c_void_p(xs.data_ptr()),
-                                                   ctypes.c_void_p(vs.data_ptr()),
-                                                   ctypes.c_void_p(main.cuda_stream)), "get_state")
-            computed[slot].record(main)
-            with torch.cuda.stream(cs):                      # D2H on the side stream
-                cs.wait_event(computed[slot])
-                hb = hostbuf[slot]
-                hb["x"].copy_(xs, non_blocking=True)
-                hb["v"].copy_(vs, non_blocking=True)
-                hb["color"].copy_(devbuf[slot][0], non_blocking=True)
-                hb["depth"].copy_(devbuf[slot][1], non_blocking=True)
-                copied[slot].record(cs)
+        def run_e2e(fmt, base_i):
+            hostbuf, devbuf = [], []
+            for slot in range(2):
+                hb = dict(x=torch.empty((E, N, 3)).pin_memory(), v=torch.empty((E, N, 3)).pin_memory(),
+                          depth=torch.empty(env.depth.shape).pin_memory())
+                color = env.color if slot == 0 else torch.empty_like(env.color)
+                depth = env.depth if slot == 0 else torch.empty_like(env.depth)
+                if fmt == "u8":
+                    hb["rgb8"] = torch.empty((env.B, H, W, 3), dtype=torch.uint8).pin_memory()
+                    devbuf.append((color, depth, torch.empty((env.B, H, W, 3), dtype=torch.uint8, device=dev)))
+                else:
+                    hb["color"] = torch.empty(env.color.shape).pin_memory()
+                    devbuf.append((color, depth))
+                hostbuf.append(hb)
+            devstate = [(torch.empty((E, N, 3), device=dev), torch.empty((E, N, 3), device=dev)) for _ in range(2)]
+            d2h = sum(t.numel() * t.element_size() for t in hostbuf[0].values())
+            computed = [torch.cuda.Event() for _ in range(2)]
+            copied = [torch.cuda.Event() for _ in range(2)]
+            for ev in copied:
+                ev.record(cs)
+
+            def e2e_step(i, slot):
+                m = upload(i)                                    # H2D: gripper tables (pinned -> device)
+                env.view.copy_(env.view_h, non_blocking=True)    # H2D: cameras
+                env.proj.copy_(env.proj_h, non_blocking=True)
+                env.campos.copy_(env.campos_h, non_blocking=True)
+                main.wait_event(copied[slot])                    # the buffers of step i-2 have left the device
+                env.step(m, out=devbuf[slot])
+                xs, vs = devstate[slot]
+                _lib.check(phys_lib.r2s_phys_get_state(env.phys.h, ctypes.c_void_p(xs.data_ptr()),
+                                                       ctypes.c_void_p(vs.data_ptr()),
+                                                       ctypes.c_void_p(main.cuda_stream)), "get_state")
+                computed[slot].record(main)
+                with torch.cuda.stream(cs):                      # D2H on the side stream
+                    cs.wait_event(computed[slot])
+                    hb = hostbuf[slot]
+                    hb["x"].copy_(xs, non_blocking=True)
+                    hb["v"].copy_(vs, non_blocking=True)
+                    hb["depth"].copy_(devbuf[slot][1], non_blocking=True)
+                    if fmt == "u8":
+                        hb["rgb8"].copy_(devbuf[slot][2], non_blocking=True)
+                    else:
+                        hb["color"].copy_(devbuf[slot][0], non_blocking=True)
+                    copied[slot].record(cs)
+
+            for i in range(args.warmup):
+                e2e_step(base_i + i, i % 2)
+            cs.synchronize()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(main)
+            for i in range(args.steps):
+                e2e_step(base_i + args.warmup + i, i % 2)
+            main.wait_stream(cs)                                 # all copies have landed
+            e1.record(main)
+            cs.synchronize()
+            barrier()
+            ms = shard.max_over_ranks(e0.elapsed_time(e1), dev)
+            last = hostbuf[(args.steps - 1) % 2]
+            out = {"value": world * E * args.steps / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                   "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / args.steps,
+                   "observations": ("rgb uint8 [B,H,W,3] (reference host format, eval_policy.py:248) + depth f32 "
+                                    "+ particle x,v f32" if fmt == "u8" else
+                                    "colour f32 [B,3,H,W] + depth f32 + particle x,v f32"),
+                   "overlap": "D2H of step k on a side stream under the compute of step k+1 (double-buffered outputs)"}
+            if fmt == "u8":
+                out["checksum_rgb8_host"] = int(last["rgb8"].long().sum())
+            else:
+                out["checksum_rgb_host"] = float(last["color"].double().sum())
+            return out
 
         base_i = args.warmup + args.steps
-        for i in range(args.warmup):
-            e2e_step(base_i + i, i % 2)
-        cs.synchronize()
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(main)
-        for i in range(args.steps):
-            e2e_step(base_i + args.warmup + i, i % 2)
-        main.wait_stream(cs)                                 # all copies have landed
-        e1.record(main)
-        cs.synchronize()
-        barrier()
-        ms_e2e = e0.elapsed_time(e1)
-        ms_e2e = shard.max_over_ranks(ms_e2e, dev)
-        last = hostbuf[(args.steps - 1) % 2]
-        e2e = {"value": world * E * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
-               "overlap": "D2H of step k on a side stream under the compute of step k+1 (double-buffered outputs)",
-               "checksum_rgb_host": float(last["color"].double().sum())}
+        e2e_f32 = run_e2e("f32", base_i)
+        e2e = run_e2e("u8", base_i + args.warmup + args.steps)
+        e2e["float_image_variant"] = e2e_f32
 
     clocks = sampler.stop()
     # ---- metrics all-gather (the only collective)

@@ -60,6 +60,9 @@ typedef struct r2s_raster_args {
     float* out_color; /* [B,3,H,W] */
     float* out_depth; /* [B,1,H,W] */
     int32_t* radii;   /* [B,P] or NULL */
+    uint8_t* out_rgb8; /* [B,H,W,3] or NULL: the host-side image format of the reference's evaluation loop,
+                          (clamp(color, 0, 1) * 255) truncated to uint8, HWC (gs_renderer.py:949 +
+                          experiments/eval_policy.py:248), written by the same kernel as out_color */
     /* scratch (caller-owned); size from r2s_raster_workspace_bytes */
     void* workspace;
     size_t workspace_bytes;

@@ -48,7 +48,7 @@ class RasterArgs(C.Structure):  # include/r2s_raster.h: r2s_raster_args
         ("means3D", c_vp), ("scales", c_vp), ("rotations", c_vp), ("opacities", c_vp), ("shs", c_vp),
         ("colors_precomp", c_vp), ("cov3D_precomp", c_vp),
         ("viewmatrix", c_vp), ("projmatrix", c_vp), ("campos", c_vp), ("bg", c_vp),
-        ("out_color", c_vp), ("out_depth", c_vp), ("radii", c_vp),
+        ("out_color", c_vp), ("out_depth", c_vp), ("radii", c_vp), ("out_rgb8", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_sz), ("max_instances", c_i64),
     ]
 

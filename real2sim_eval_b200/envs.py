@@ -157,8 +157,11 @@ class BatchedEnv:
     def step(self, motion=None, out=None):
         """One frame for every env: [gripper tables ->] collision graph -> substeps -> LBS -> render.
         `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None.
-        `out`: optional (color, depth) device tensors to render into (double buffering)."""
-        color, depth = out if out is not None else (self.color, self.depth)
+        `out`: optional (color, depth[, rgb8]) device tensors to render into (double buffering); rgb8 is
+        the [B,H,W,3] uint8 image the reference's evaluation loop builds on the host
+        (experiments/eval_policy.py:248), written here by the compositing kernel."""
+        color, depth = (out[0], out[1]) if out is not None else (self.color, self.depth)
+        rgb8 = out[2] if out is not None and len(out) > 2 else None
         if self.phys.self_collision:
             self.phys.update_collision_graph()       # once per frame (phystwin.py:365-366)
         if motion is not None:
@@ -172,6 +175,6 @@ class BatchedEnv:
                             tanfovy=self.cams[0].tanfovy, shs=self.shs, scales=self.scales, rotations=self.rotations,
                             sh_degree=0, z_threshold=0.05, views_per_scene=c.cameras,
                             max_instances=self.max_instances, out_color=color, out_depth=depth,
-                            want_radii=False)
+                            want_radii=False, out_rgb8=rgb8)
         self.frame += 1
         return color, depth

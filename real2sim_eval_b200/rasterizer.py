@@ -82,7 +82,7 @@ class BatchedRasterizer:
     def forward(self, means3D, opacities, *, viewmatrix, projmatrix, campos, bg, W, H, tanfovx, tanfovy,
                 shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, sh_degree=0,
                 scale_modifier=1.0, z_threshold=0.05, prefiltered=False, views_per_scene=1,
-                max_instances=None, out_color=None, out_depth=None, radii=None, want_radii=True):
+                max_instances=None, out_color=None, out_depth=None, radii=None, want_radii=True, out_rgb8=None):
         dev = self.device
         means3D = _f32c(means3D, dev)
         viewmatrix = _f32c(viewmatrix, dev).reshape(-1, 16)
@@ -119,6 +119,10 @@ class BatchedRasterizer:
         a.shs, a.colors_precomp, a.cov3D_precomp = _ptr(shs), _ptr(colors_precomp), _ptr(cov3D_precomp)
         a.viewmatrix, a.projmatrix, a.campos, a.bg = _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), _ptr(bg)
         a.out_color, a.out_depth, a.radii = _ptr(out_color), _ptr(out_depth), _ptr(radii)
+        if out_rgb8 is not None:   # optional [B,H,W,3] uint8 image (the reference's host-side format)
+            if out_rgb8.dtype != torch.uint8 or not out_rgb8.is_contiguous() or out_rgb8.numel() != B * H * W * 3:
+                raise ValueError("out_rgb8 must be a contiguous uint8 tensor of shape [B,H,W,3]")
+            a.out_rgb8 = _ptr(out_rgb8)
         a.workspace, a.workspace_bytes, a.max_instances = _ptr(self.ws), self.ws.numel(), self.max_instances
         with torch.cuda.device(dev):
             _lib.check(self.lib.r2s_raster_forward(C.byref(a), _stream_ptr(dev)), "r2s_raster_forward")

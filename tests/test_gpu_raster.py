@@ -379,3 +379,37 @@ def test_scale_modifier_and_prefiltered_flag():
     assert (radii == orad).mean() > 0.995 and radii.max() > 0
     _close_images(color, oc, "scale_modifier 1.7")
     _close_images(depth, od, "scale_modifier 1.7 depth")
+
+
+def test_rgb8_output_is_the_reference_host_conversion():
+    """out_rgb8 == (clamp(color, 0, 1).permute(1, 2, 0) * 255).astype(uint8), byte for byte
+    (sim/renderer/gs_renderer.py:949 + experiments/eval_policy.py:248), including colours above 1
+    (bright SH terms) and a non-multiple-of-16 image size."""
+    import torch
+    g = _util.small_gaussians(37, 3000)
+    g["shs"] = (g["shs"] * 3.0).astype(np.float32)      # push some pixels outside [0, 1]
+    cam = _util.make_test_camera(136, 88)
+    B = 2
+    rgb8 = torch.full((B, cam.H, cam.W, 3), 7, dtype=torch.uint8, device="cuda")
+    from real2sim_eval_b200.rasterizer import BatchedRasterizer
+    r = BatchedRasterizer("cuda")
+    t = _torchify(g)
+    view = torch.tensor(np.stack([cam.view] * B)).cuda()
+    proj = torch.tensor(np.stack([cam.proj] * B)).cuda()
+    campos = torch.tensor(np.stack([cam.campos] * B)).cuda()
+    color, _, _ = r.forward(t["means3D"], t["opacities"], viewmatrix=view, projmatrix=proj, campos=campos,
+                            bg=torch.tensor([0.2, 0.4, 1.5]).cuda(), W=cam.W, H=cam.H, tanfovx=cam.tanfovx,
+                            tanfovy=cam.tanfovy, shs=t["shs"], scales=t["scales"], rotations=t["rotations"],
+                            z_threshold=cam.z_threshold, views_per_scene=B,
+                            max_instances=64 * B * len(g["means3D"]) + 4096, out_rgb8=rgb8)
+    assert r.status()[1] == 0
+    c = color.cpu().numpy()
+    assert (c > 1.0).any() and (c < 0.0).any() or (c > 1.0).any()
+    want = (np.clip(c, 0.0, 1.0).transpose(0, 2, 3, 1) * 255).astype(np.uint8)
+    got = rgb8.cpu().numpy()
+    assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        r.forward(t["means3D"], t["opacities"], viewmatrix=view, projmatrix=proj, campos=campos,
+                  bg=torch.zeros(3).cuda(), W=cam.W, H=cam.H, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
+                  shs=t["shs"], scales=t["scales"], rotations=t["rotations"], views_per_scene=B,
+                  out_rgb8=torch.empty((B, cam.H, cam.W, 3), dtype=torch.float32, device="cuda"))

@@ -148,7 +148,8 @@ def run_ours(args):
     lib = _lib.load()
     E, ns = cfg.E, cfg.n_substeps
     n_frames = args.warmup + args.steps + (0 if args.no_e2e else 2 * (args.warmup + args.steps)) + 2
-    acts = [env.make_actions(f) for f in range(n_frames)]           # host numpy, made before any timing
+    # host numpy, made before any timing: gripper tables + the robot's FK link poses of every frame
+    acts = [env.make_actions(f) + (env.make_link_poses(f),) for f in range(n_frames)]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     acts_pinned = [tuple(pin(a) for a in act) for act in acts]
     dev_bufs = tuple(torch.empty_like(t, device=dev) for t in acts_pinned[0])
@@ -172,7 +173,7 @@ def run_ours(args):
     time.sleep(1.0)                 # let nvidia-smi start streaming before the measured span
     sampler.mark()
     for i in range(args.warmup):
-        env.step(motions_dev[i])
+        env.step(motions_dev[i][:4], link_pose=motions_dev[i][4])
     total, overflow = env.raster.status()
     if overflow:
         raise RuntimeError(f"instance capacity exceeded ({total} > {env.max_instances})")
@@ -185,6 +186,7 @@ def run_ours(args):
     pe0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     pe1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     pe2 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pe3 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     import ctypes
     prof = (ctypes.c_float * 5)()
     ev0.record()
@@ -193,13 +195,15 @@ def run_ours(args):
         # (same body as env.step, with events around the physics launch for the per-kernel report)
         if env.phys.self_collision:
             env.phys.update_collision_graph()
-        env.phys.set_mesh_motion(*m)
+        env.phys.set_mesh_motion(*m[:4])
         env.x_prev4.copy_(env.phys.x4)
         pe0[k].record()
         env.phys.step()
         pe1[k].record()
         env.lbs.forward(env.x_prev4, env.phys.x4, env.means3D)
         pe2[k].record()
+        env.links.forward(m[4], env.means3D, env.rotations)
+        pe3[k].record()
         env.raster.forward(env.means3D, env.opacities, viewmatrix=env.view, projmatrix=env.proj, campos=env.campos,
                            bg=env.bg, W=W, H=H, tanfovx=env.cams[0].tanfovx, tanfovy=env.cams[0].tanfovy, shs=env.shs,
                            scales=env.scales, rotations=env.rotations, sh_degree=0, z_threshold=0.05,
@@ -213,6 +217,7 @@ def run_ours(args):
     stage_ms = np.array(list(prof), dtype=np.float64)
     phys_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe0, pe1)]))
     lbs_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe1, pe2)]))
+    links_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe2, pe3)]))
     lib.r2s_raster_set_profile(0)
     total, overflow = env.raster.status()
     from real2sim_eval_b200 import shard
@@ -257,12 +262,12 @@ def run_ours(args):
                 ev.record(cs)
 
             def e2e_step(i, slot):
-                m = upload(i)                                    # H2D: gripper tables (pinned -> device)
+                m = upload(i)                                    # H2D: gripper tables + link poses (pinned -> device)
                 env.view.copy_(env.view_h, non_blocking=True)    # H2D: cameras
                 env.proj.copy_(env.proj_h, non_blocking=True)
                 env.campos.copy_(env.campos_h, non_blocking=True)
                 main.wait_event(copied[slot])                    # the buffers of step i-2 have left the device
-                env.step(m, out=devbuf[slot])
+                env.step(m[:4], out=devbuf[slot], link_pose=m[4])
                 xs, vs = devstate[slot]
                 _lib.check(phys_lib.r2s_phys_get_state(env.phys.h, ctypes.c_void_p(xs.data_ptr()),
                                                        ctypes.c_void_p(vs.data_ptr()),
@@ -324,12 +329,13 @@ def run_ours(args):
     alg = {
         "phys_frame": E * ns * (52 * env.base.N + 16 * env.base.S),
         "lbs": E * env.base.N * (32 + 36) + E * env.n_obj * 24 + env.n_obj * env.K * 8 + env.base.N * cfg.k_rel * 4,
+        "links": E * env.n_robot * 28 + env.n_robot * 32 + E * env.links.L * 64,
         "preprocess": B * P * (44 + 12 * 1) + B * P * 40,
         "emit": R * 12,
         "tile_sort": R * 24,
         "composite": R * 40 + B * W * H * 16,
     }
-    times = {"phys_frame": phys_ms, "lbs": lbs_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
+    times = {"phys_frame": phys_ms, "lbs": lbs_ms, "links": links_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
              "tile_sort": stage_ms[3], "composite": stage_ms[4]}
     dom = max(alg, key=lambda k: times[k])   # dominant kernel among those with an algorithmic-byte model
     ach = alg[dom] / (times[dom] / 1e3) / 1e9
@@ -354,6 +360,7 @@ def run_ours(args):
                                f"render of {P} Gaussians per env (BASELINE configs[1])",
                    "envs_per_gpu": E, "global_envs": world * E, "particles": env.base.N, "springs": env.base.S,
                    "substeps": ns, "resolution": [W, H], "cameras": cfg.cameras, "gaussians_per_env": P,
+                   "gaussian_rows": {"object_lbs": env.n_obj, "robot_links": env.n_robot, "static": P - env.n_obj - env.n_robot},
                    "instances_per_step": int(R), "instances_per_gaussian": round(R / (B * P), 3),
                    "super_tile_instances_per_step": int(env.raster.intermediates()["super_offset"][-1].item()),
                    "mean_tile_list": round(R / (B * T), 1), "parallelism": f"env-shard x{world}",

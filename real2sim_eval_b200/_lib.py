@@ -53,6 +53,14 @@ class RasterArgs(C.Structure):  # include/r2s_raster.h: r2s_raster_args
     ]
 
 
+class LinksArgs(C.Structure):  # include/r2s_links.h: r2s_links_args
+    _fields_ = [
+        ("E", c_i32), ("L", c_i32), ("P", c_i32), ("first", c_i32), ("n_robot", c_i32), ("pad0_", c_i32),
+        ("link_id", c_vp), ("rest_means", c_vp), ("rest_quats", c_vp), ("link_pose", c_vp), ("link_offset", c_vp),
+        ("rest_inv", c_vp), ("means3D", c_vp), ("rotations", c_vp), ("link_scratch", c_vp),
+    ]
+
+
 class LbsArgs(C.Structure):  # include/r2s_lbs.h: r2s_lbs_args
     _fields_ = [
         ("E", c_i32), ("N", c_i32), ("P", c_i32), ("n_obj", c_i32), ("k_rel", c_i32), ("k_wgt", c_i32),
@@ -95,6 +103,7 @@ SYMBOLS = [
     ("r2s_raster_set_profile", C.c_int, [c_i32]),
     ("r2s_raster_get_profile", C.c_int, [C.POINTER(c_f * 5)]),
     ("r2s_lbs_forward", C.c_int, [C.POINTER(LbsArgs), c_vp]),
+    ("r2s_links_forward", C.c_int, [C.POINTER(LinksArgs), c_vp]),
 ]
 
 _lib = None

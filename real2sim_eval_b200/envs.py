@@ -19,6 +19,7 @@ import torch
 
 from . import _lib, synth
 from .lbs import BatchedLBS
+from .links import BatchedLinkTransform
 from .physics import BatchedSpringMass
 from .rasterizer import BatchedRasterizer
 
@@ -37,6 +38,7 @@ class EnvBatchConfig:
     n_substeps: int = 10
     P: int = 200_000             # Gaussians per environment
     obj_frac: float = 0.1        # fraction bound to the particles
+    robot_frac: float = 0.15     # fraction that is the robot scan, re-posed per frame from link poses (N2)
     knn: int = 16                # bones per Gaussian (gs_renderer.py:35 k_wgt)
     k_rel: int = 8               # neighbours per bone (gs_renderer.py:34 k_rel)
     seed: int = 1234
@@ -107,6 +109,19 @@ class BatchedEnv:
         rel = tree.query(base.x, k=cfg.k_rel + 1)[1][:, 1:]        # gs_renderer.py:195-200 knn_relations
         self.lbs = BatchedLBS(E, base.N, P, n_obj, rel, w, idx.reshape(n_obj, self.K), device=dev)
         self.x_prev4 = torch.empty_like(self.phys.x4)
+        # robot scan: rows [n_obj, n_obj + n_robot) of every env, one shared scan, per-env link poses
+        self.n_robot = int(P * cfg.robot_frac)
+        self.links = None
+        if self.n_robot:
+            self.scan = synth.make_robot_scan(self.n_robot, cfg.seed, origin=(0.3, -0.3, 0.05),
+                                              volume=([-0.1, -0.6, 0.0], [1.1, 0.6, 0.6]))
+            self.links = BatchedLinkTransform(E, P, n_obj, self.scan.link_id, self.scan.points, self.scan.quats,
+                                              self.scan.link_offset, self.scan.base_pose, device=dev)
+            base = self.scan.base_pose
+            prev = np.concatenate([np.eye(4)[None], base[:-1]])
+            self._joint_rel = np.linalg.inv(prev) @ base                       # (L,4,4) joint frames at rest
+            self._joint_phase = np.random.default_rng(cfg.seed + 5).uniform(0, 6.28, (E + cfg.env_offset, len(base), 3))[cfg.env_offset:]
+            self.link_pose = torch.tensor(self.make_link_poses(0), device=dev)
         for e in range(E):
             gen.manual_seed(cfg.seed + 7 * (cfg.env_offset + e) + 1)
             means[e] = lo + (hi - lo) * torch.rand((P, 3), device=dev, generator=gen)
@@ -117,6 +132,8 @@ class BatchedEnv:
             shs[e] = (torch.rand((P, 1, 3), device=dev, generator=gen) - 0.5) / 0.28209479177387814
             means[e, :n_obj] = torch.tensor(synth.pose_points(src, pose_tf[e]), device=dev)   # posed with the env's object
         self.means3D, self.scales, self.rotations, self.opacities, self.shs = means, scales, rots, opac, shs
+        if self.links is not None:
+            self.links.forward(self.link_pose, self.means3D, self.rotations)
         # cameras: cfg.cameras fixed views per env (side, and a top-down second view), small per-env jitter
         cams = []
         for e in range(E):
@@ -154,9 +171,29 @@ class BatchedEnv:
         self.finger_pose = self.finger_pose + vel * np.float32(self.dt * ns)
         return pts, ctr, dyn_vel, dyn_omega
 
-    def step(self, motion=None, out=None):
-        """One frame for every env: [gripper tables ->] collision graph -> substeps -> LBS -> render.
+    def make_link_poses(self, frame: int) -> np.ndarray:
+        """(E, L, 4, 4) float32 FK poses of every env's robot links for this frame: each joint of the chain
+        swings smoothly about its rest frame (stand-in for sapien FK of the policy's qpos,
+        robot_pc_sampler.py:131-136)."""
+        ang = 0.05 * np.sin(self._joint_phase + 0.15 * frame)                  # (E,L,3) rotation vectors
+        th = np.linalg.norm(ang, axis=-1)[..., None, None]
+        k = ang / np.maximum(th[..., 0], 1e-12)
+        K = np.zeros(ang.shape[:2] + (3, 3))
+        K[..., 0, 1], K[..., 0, 2], K[..., 1, 0] = -k[..., 2], k[..., 1], k[..., 2]
+        K[..., 1, 2], K[..., 2, 0], K[..., 2, 1] = -k[..., 0], -k[..., 1], k[..., 0]
+        J = np.tile(np.eye(4), ang.shape[:2] + (1, 1))
+        J[..., :3, :3] = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+        out = np.empty_like(J)
+        cur = np.tile(np.eye(4), (ang.shape[0], 1, 1))
+        for s in range(ang.shape[1]):
+            cur = cur @ J[:, s] @ self._joint_rel[s]
+            out[:, s] = cur
+        return out.astype(np.float32)
+
+    def step(self, motion=None, out=None, link_pose=None):
+        """One frame for every env: [gripper tables ->] collision graph -> substeps -> LBS -> robot links -> render.
         `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None.
+        `link_pose`: [E,L,4,4] device tensor of the robot's FK link poses for this frame, or None (robot kept).
         `out`: optional (color, depth[, rgb8]) device tensors to render into (double buffering); rgb8 is
         the [B,H,W,3] uint8 image the reference's evaluation loop builds on the host
         (experiments/eval_policy.py:248), written here by the compositing kernel."""
@@ -169,6 +206,8 @@ class BatchedEnv:
         self.x_prev4.copy_(self.phys.x4)             # state['x'] before the frame (gs_renderer.py:727)
         self.phys.step()
         self.lbs.forward(self.x_prev4, self.phys.x4, self.means3D)
+        if self.links is not None and link_pose is not None:   # robot Gaussians follow this frame's FK poses
+            self.links.forward(link_pose, self.means3D, self.rotations)
         c = self.cfg
         self.raster.forward(self.means3D, self.opacities, viewmatrix=self.view, projmatrix=self.proj,
                             campos=self.campos, bg=self.bg, W=c.W, H=c.H, tanfovx=self.cams[0].tanfovx,

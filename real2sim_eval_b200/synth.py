@@ -397,3 +397,82 @@ def make_gaussians(seed: int, P: int = 200_000, particles: np.ndarray | None = N
     shs = (rgb - 0.5) / 0.28209479177387814
     f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
     return Gaussians(f32(means), f32(scales), f32(q), f32(opa), f32(shs), n_object, bind_idx, bind_w)
+
+
+# ---------------------------------------------------------------------------- robot scan
+XARM_LINK_IDS = (1, 2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13, 14, 15, 16)   # robot_pc_transformations.py:35
+XARM_N_LINKS = 18                                                      # :34 (0: world, 9: link_eef, 17: link_tcp)
+
+
+def _rot_from_rotvec(r):
+    r = np.asarray(r, np.float64)
+    th = np.linalg.norm(r)
+    if th < 1e-12:
+        return np.eye(3)
+    k = r / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def _rigid(rotvec, t):
+    m = np.eye(4)
+    m[:3, :3] = _rot_from_rotvec(rotvec)
+    m[:3, 3] = t
+    return m
+
+
+@dataclass
+class RobotScan:
+    """A synthetic stand-in for the scanned robot Gaussians and their link bookkeeping (the real scan and the
+    URDF are not shipped): a serial chain of 15 moving links above the table."""
+    link_names: list
+    total_mask: np.ndarray      # (n,) float32 link index per Gaussian, as total_mask_path stores it (gs_renderer.py:505-506)
+    link_id: np.ndarray         # (n,) int32 slot in XARM_LINK_IDS order, -1 if the link is not listed
+    points: np.ndarray          # (n,3) float32 rest positions (at base_qpos)
+    quats: np.ndarray           # (n,4) float32 w,x,y,z, un-normalised
+    link_offset: np.ndarray     # (15,4,4) float64 tf_obj_to_link
+    base_pose: np.ndarray       # (15,4,4) float64 FK pose at base_qpos
+
+
+def make_robot_scan(n: int = 30_000, seed: int = 1234, origin=(-0.25, 0.0, 0.05), volume=None) -> RobotScan:
+    """`volume=(lo, hi)`: rest positions uniform in that box instead of clustered around the links (keeps the
+    bench's Gaussian density that of SURVEY.md §8d while the rows still move rigidly with their links)."""
+    rng = np.random.default_rng(seed)
+    names = ["world", "link_base"] + [f"link{i}" for i in range(1, 8)] + ["link_eef"] + \
+            [f"finger{i}" for i in range(7)] + ["link_tcp"]
+    L = len(XARM_LINK_IDS)
+    base_pose = np.zeros((L, 4, 4))
+    offs = np.zeros((L, 4, 4))
+    cur = _rigid((0, 0, 0), origin)
+    for s in range(L):
+        cur = cur @ _rigid(rng.normal(0, 0.4, 3), rng.uniform(0.02, 0.09, 3) * (1 if s < 9 else 0.3))
+        base_pose[s] = cur
+        offs[s] = _rigid(rng.normal(0, 0.2, 3), rng.normal(0, 0.01, 3))
+    # a few Gaussians belong to links that never move (world / link_eef / link_tcp): they keep their place
+    mask = rng.choice(np.arange(XARM_N_LINKS), size=n, p=np.r_[0.03, np.full(8, 0.08), 0.01, np.full(7, 0.045), 0.005])
+    slot_of = -np.ones(XARM_N_LINKS, np.int32)
+    slot_of[list(XARM_LINK_IDS)] = np.arange(L, dtype=np.int32)
+    link_id = slot_of[mask]
+    local = rng.normal(0, 0.025, (n, 3))
+    centre = np.where(link_id[:, None] >= 0, (base_pose @ offs)[np.maximum(link_id, 0), :3, 3], np.asarray(origin)[None])
+    points = (centre + local).astype(np.float32)
+    if volume is not None:
+        lo, hi = np.asarray(volume[0], np.float64), np.asarray(volume[1], np.float64)
+        points = (lo + (hi - lo) * rng.random((n, 3))).astype(np.float32)
+    quats = (rng.normal(0, 1, (n, 4)) * rng.uniform(0.5, 2.0, (n, 1))).astype(np.float32)
+    return RobotScan(names, mask.astype(np.float32), link_id.astype(np.int32), points, quats, offs, base_pose)
+
+
+def robot_link_poses(scan: RobotScan, seed: int, amount: float = 0.3) -> np.ndarray:
+    """(15,4,4) float64 FK poses of one frame: every joint of the chain turned by a seeded angle, so the
+    links move rigidly and coherently (what sapien's FK would return for some qpos)."""
+    rng = np.random.default_rng(seed)
+    L = len(scan.base_pose)
+    out = np.zeros_like(scan.base_pose)
+    prev_base, prev_new = np.eye(4), np.eye(4)
+    for s in range(L):
+        rel = np.linalg.inv(prev_base) @ scan.base_pose[s]           # joint frame at rest
+        new = prev_new @ _rigid(rng.normal(0, amount, 3), rng.normal(0, 0.002, 3)) @ rel
+        out[s] = new
+        prev_base, prev_new = scan.base_pose[s], new
+    return out

@@ -15,8 +15,18 @@ def test_sloth_two_cameras_640x480():
     assert env.phys.smem_state, "3500 particles x 44 B still fit the 227 KB shared memory"
     acts = [tuple(torch.tensor(a).cuda() for a in env.make_actions(f)) for f in range(3)]
     x0 = env.phys.get_state()[0].clone()
-    for m in acts:
-        color, depth = env.step(m)
+    rest_rows = env.means3D[:, env.n_obj:env.n_obj + env.n_robot].clone()
+    for f, m in enumerate(acts):
+        lp = torch.tensor(env.make_link_poses(f + 1)).cuda()
+        color, depth = env.step(m, link_pose=lp)
+    # robot rows follow this frame's link poses (N2) and match the oracle for env 2
+    from oracle import links_ref
+    sc = env.scan
+    p, q = links_ref.transform_gs(sc.points, sc.quats, sc.link_id, lp[2].cpu().numpy(), sc.base_pose, sc.link_offset)
+    rows = slice(env.n_obj, env.n_obj + env.n_robot)
+    assert np.abs(env.means3D[2, rows].cpu().numpy() - p).max() < 2e-6
+    assert np.abs(env.rotations[2, rows].cpu().numpy() - q).max() < 2e-6
+    assert not torch.equal(env.means3D[:, rows], rest_rows)
     total, overflow = env.raster.status()
     assert not overflow and total > 0
     assert tuple(color.shape) == (6, 3, 480, 640) and tuple(depth.shape) == (6, 1, 480, 640)

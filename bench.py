@@ -9,13 +9,14 @@
 Workload (BASELINE.json configs[1]): rope PhysTwin (synthetic, N=2048 particles / S=32889
 springs), 256 parallel envs per GPU, 10 substeps per step, one 512x512 RGB-D render per env of
 200,000 Gaussians (10% bound to the particles).  A step is one pass of the hot path over all
-envs: per-frame collision-graph rebuild -> 10 substeps -> LBS of the object Gaussians -> render.
+envs: end-effector command -> per-substep finger tables + grasp hysteresis (device) -> per-frame
+collision-graph rebuild -> 10 substeps -> LBS of the object Gaussians -> robot link re-posing -> render.
 Multi-GPU: envs shard statically, one process per GPU, no data-path collective; one NCCL
 all-gather of {steps, seconds, checksum(x), checksum(rgb)} at the end (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput (CUDA events, max over
-ranks); `e2e` is the same loop driven from HOST buffers: per step the gripper-motion tables and
-camera matrices are copied from pinned host memory, and particle states + rendered RGB-D are
+ranks); `e2e` is the same loop driven from HOST buffers: per step the end-effector commands, the
+robot's link poses and the camera matrices are copied from pinned host memory, and particle states + rendered RGB-D are
 copied back to pinned host memory, all inside the timed region.
 
 `--impl reference` times the reference pipeline on the same box: the CPU restatement of
@@ -148,8 +149,8 @@ def run_ours(args):
     lib = _lib.load()
     E, ns = cfg.E, cfg.n_substeps
     n_frames = args.warmup + args.steps + (0 if args.no_e2e else 2 * (args.warmup + args.steps)) + 2
-    # host numpy, made before any timing: gripper tables + the robot's FK link poses of every frame
-    acts = [env.make_actions(f) + (env.make_link_poses(f),) for f in range(n_frames)]
+    # host numpy, made before any timing: end-effector commands (19 floats per env) + the robot's FK link poses of every frame
+    acts = [env.make_commands(f) + (env.make_link_poses(f),) for f in range(n_frames)]
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     acts_pinned = [tuple(pin(a) for a in act) for act in acts]
     dev_bufs = tuple(torch.empty_like(t, device=dev) for t in acts_pinned[0])
@@ -173,7 +174,7 @@ def run_ours(args):
     time.sleep(1.0)                 # let nvidia-smi start streaming before the measured span
     sampler.mark()
     for i in range(args.warmup):
-        env.step(motions_dev[i][:4], link_pose=motions_dev[i][4])
+        env.step(command=motions_dev[i][:5], link_pose=motions_dev[i][5])
     total, overflow = env.raster.status()
     if overflow:
         raise RuntimeError(f"instance capacity exceeded ({total} > {env.max_instances})")
@@ -187,6 +188,7 @@ def run_ours(args):
     pe1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     pe2 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     pe3 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pem = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     import ctypes
     prof = (ctypes.c_float * 5)()
     ev0.record()
@@ -195,14 +197,15 @@ def run_ours(args):
         # (same body as env.step, with events around the physics launch for the per-kernel report)
         if env.phys.self_collision:
             env.phys.update_collision_graph()
-        env.phys.set_mesh_motion(*m[:4])
+        pem[k].record()
+        env.eef.forward(*m[:5])
         env.x_prev4.copy_(env.phys.x4)
         pe0[k].record()
         env.phys.step()
         pe1[k].record()
         env.lbs.forward(env.x_prev4, env.phys.x4, env.means3D)
         pe2[k].record()
-        env.links.forward(m[4], env.means3D, env.rotations)
+        env.links.forward(m[5], env.means3D, env.rotations)
         pe3[k].record()
         env.raster.forward(env.means3D, env.opacities, viewmatrix=env.view, projmatrix=env.proj, campos=env.campos,
                            bg=env.bg, W=W, H=H, tanfovx=env.cams[0].tanfovx, tanfovy=env.cams[0].tanfovy, shs=env.shs,
@@ -218,6 +221,7 @@ def run_ours(args):
     phys_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe0, pe1)]))
     lbs_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe1, pe2)]))
     links_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe2, pe3)]))
+    eef_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pem, pe0)]))   # incl. the x_prev copy
     lib.r2s_raster_set_profile(0)
     total, overflow = env.raster.status()
     from real2sim_eval_b200 import shard
@@ -262,12 +266,12 @@ def run_ours(args):
                 ev.record(cs)
 
             def e2e_step(i, slot):
-                m = upload(i)                                    # H2D: gripper tables + link poses (pinned -> device)
+                m = upload(i)                                    # H2D: end-effector commands + link poses (pinned -> device)
                 env.view.copy_(env.view_h, non_blocking=True)    # H2D: cameras
                 env.proj.copy_(env.proj_h, non_blocking=True)
                 env.campos.copy_(env.campos_h, non_blocking=True)
                 main.wait_event(copied[slot])                    # the buffers of step i-2 have left the device
-                env.step(m[:4], out=devbuf[slot], link_pose=m[4])
+                env.step(command=m[:5], out=devbuf[slot], link_pose=m[5])
                 xs, vs = devstate[slot]
                 _lib.check(phys_lib.r2s_phys_get_state(env.phys.h, ctypes.c_void_p(xs.data_ptr()),
                                                        ctypes.c_void_p(vs.data_ptr()),
@@ -335,7 +339,8 @@ def run_ours(args):
         "tile_sort": R * 24,
         "composite": R * 40 + B * W * H * 16,
     }
-    times = {"phys_frame": phys_ms, "lbs": lbs_ms, "links": links_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
+    alg["eef"] = E * (19 * 4 + ns * (env.eef.V + 1) * 12 + 36 + env.eef.V * 24)   # command in, tables out (+ 2 table rows)
+    times = {"eef": eef_ms, "phys_frame": phys_ms, "lbs": lbs_ms, "links": links_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
              "tile_sort": stage_ms[3], "composite": stage_ms[4]}
     dom = max(alg, key=lambda k: times[k])   # dominant kernel among those with an algorithmic-byte model
     ach = alg[dom] / (times[dom] / 1e3) / 1e9

@@ -97,6 +97,19 @@ int r2s_phys_set_mesh_motion(r2s_phys* h, const float* interp_pts, const float* 
                              const float* dyn_vel, const float* dyn_omega, int per_env,
                              void* stream);
 
+/* The handle's own motion tables, for a producer that fills them in place on the device each frame
+ * (r2s_eef_forward) instead of copying through r2s_phys_set_mesh_motion.  Shapes as in
+ * r2s_phys_set_mesh_motion with dyn_vel always [(E,) 2, 3].  Switching per_env re-allocates (contents
+ * undefined until written); the pointers stay valid until the next r2s_phys_set_mesh / switch. */
+typedef struct r2s_phys_motion {
+    float* interp_pts;    /* [n_env, n_substeps, n_dyn_verts, 3] */
+    float* interp_center; /* [n_env, n_substeps, 3]              */
+    float* dyn_vel;       /* [n_env, 2, 3]                       */
+    float* dyn_omega;     /* [n_env, 3]                          */
+    int32_t n_env, n_substeps, n_dyn_verts, dyn_vel_rows;
+} r2s_phys_motion;
+int r2s_phys_motion_ptrs(r2s_phys* h, int per_env, r2s_phys_motion* out);
+
 /* create_resting_case (SMW:729-740) from the current x. */
 int r2s_phys_create_resting_case(r2s_phys* h, void* stream);
 /* update_collision_graph (SMW:806-821): rebuild candidate lists from current x. */

@@ -61,6 +61,24 @@ class LinksArgs(C.Structure):  # include/r2s_links.h: r2s_links_args
     ]
 
 
+class EefArgs(C.Structure):  # include/r2s_eef.h: r2s_eef_args
+    _fields_ = [
+        ("E", c_i32), ("n_substeps", c_i32), ("n_pts", c_i32), ("n_table", c_i32), ("use_pusher", c_i32), ("F", c_i32),
+        ("force_faces", c_i32 * 6), ("dyn_vel_rows", c_i32), ("pad0_", c_i32),
+        ("grasp_force_threshold", c_f), ("pad1_", c_f), ("dt", C.c_double),
+        ("table", c_vp), ("init_eef_xyz", c_vp), ("eef_xyz", c_vp), ("eef_vel", c_vp), ("eef_rot", c_vp),
+        ("eef_rot_vel", c_vp), ("openness_cmd", c_vp), ("collision_forces", c_vp), ("current_openness", c_vp),
+        ("grasped", c_vp), ("interp_pts", c_vp), ("interp_center", c_vp), ("dyn_vel", c_vp), ("dyn_omega", c_vp),
+    ]
+
+
+class PhysMotion(C.Structure):  # include/r2s_phys.h: r2s_phys_motion
+    _fields_ = [
+        ("interp_pts", c_vp), ("interp_center", c_vp), ("dyn_vel", c_vp), ("dyn_omega", c_vp),
+        ("n_env", c_i32), ("n_substeps", c_i32), ("n_dyn_verts", c_i32), ("dyn_vel_rows", c_i32),
+    ]
+
+
 class LbsArgs(C.Structure):  # include/r2s_lbs.h: r2s_lbs_args
     _fields_ = [
         ("E", c_i32), ("N", c_i32), ("P", c_i32), ("n_obj", c_i32), ("k_rel", c_i32), ("k_wgt", c_i32),
@@ -90,6 +108,7 @@ SYMBOLS = [
     ("r2s_phys_set_collide", C.c_int, [c_vp, c_f, c_f, c_f, c_f, c_f, c_f]),
     ("r2s_phys_set_mesh", C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32]),
     ("r2s_phys_set_mesh_motion", C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp]),
+    ("r2s_phys_motion_ptrs", C.c_int, [c_vp, C.c_int, C.POINTER(PhysMotion)]),
     ("r2s_phys_create_resting_case", C.c_int, [c_vp, c_vp]),
     ("r2s_phys_update_collision_graph", C.c_int, [c_vp, c_vp]),
     ("r2s_phys_step", C.c_int, [c_vp, c_i32, c_vp]),
@@ -104,6 +123,7 @@ SYMBOLS = [
     ("r2s_raster_get_profile", C.c_int, [C.POINTER(c_f * 5)]),
     ("r2s_lbs_forward", C.c_int, [C.POINTER(LbsArgs), c_vp]),
     ("r2s_links_forward", C.c_int, [C.POINTER(LinksArgs), c_vp]),
+    ("r2s_eef_forward", C.c_int, [C.POINTER(EefArgs), c_vp]),
 ]
 
 _lib = None

@@ -1416,6 +1416,27 @@ int r2s_phys_set_mesh_motion(r2s_phys* h, const float* interp_pts, const float* 
     return R2S_OK;
 }
 
+int r2s_phys_motion_ptrs(r2s_phys* h, int per_env, r2s_phys_motion* out)
+{
+    R2S_REQUIRE(h && h->F > 0, "r2s_phys_motion_ptrs: no mesh set");
+    R2S_REQUIRE(out, "r2s_phys_motion_ptrs: null output");
+    const int ne = per_env ? h->d.E : 1, ns = h->d.n_substeps;
+    if (h->motion_per_env != (per_env ? 1 : 0)) {   // re-shape the tables; contents start undefined
+        cudaFree(h->interp_pts); cudaFree(h->interp_center); cudaFree(h->dyn_vel); cudaFree(h->dyn_omega);
+        h->interp_pts = h->interp_center = h->dyn_vel = h->dyn_omega = nullptr;
+        if (dmalloc(&h->interp_pts, (size_t)ne * ns * h->n_dyn * 3) || dmalloc(&h->interp_center, (size_t)ne * ns * 3) ||
+            dmalloc(&h->dyn_vel, (size_t)ne * 6) || dmalloc(&h->dyn_omega, (size_t)ne * 3))
+            return R2S_ERR_CUDA;
+        R2S_CUDA_TRY(cudaMemset(h->dyn_vel, 0, sizeof(float) * (size_t)ne * 6));
+        R2S_CUDA_TRY(cudaMemset(h->dyn_omega, 0, sizeof(float) * (size_t)ne * 3));
+        h->motion_per_env = per_env ? 1 : 0;
+    }
+    out->interp_pts = h->interp_pts; out->interp_center = h->interp_center;
+    out->dyn_vel = h->dyn_vel; out->dyn_omega = h->dyn_omega;
+    out->n_env = ne; out->n_substeps = ns; out->n_dyn_verts = h->n_dyn; out->dyn_vel_rows = 2;
+    return R2S_OK;
+}
+
 static int run_grid(r2s_phys* h, bool resting, cudaStream_t st)
 {
     R2S_REQUIRE(h && h->d.self_collision, "self collision is disabled for this system");

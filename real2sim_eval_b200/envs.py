@@ -18,6 +18,7 @@ import numpy as np
 import torch
 
 from . import _lib, synth
+from .eef import BatchedEefMotion
 from .lbs import BatchedLBS
 from .links import BatchedLinkTransform
 from .physics import BatchedSpringMass
@@ -86,6 +87,12 @@ class BatchedEnv:
             g = self.gripper
             self.phys.set_mesh(g.verts, g.faces, g.mesh_map, g.face_map, len(g.verts))
             self.finger_pose = np.zeros((E, 3), np.float32)  # accumulated eef translation per env
+            # N3: the end-effector command -> per-substep tables + grasp hysteresis on the device, written in
+            # place into the physics handle's motion tables (phystwin.py:362-460)
+            self.eef_init = np.array([ctr[0], ctr[1], 0.004], np.float32)
+            self.eef = BatchedEefMotion(E, synth.gripper_opening_table(self.eef_init), self.eef_init, dt=pr["dt"],
+                                        n_substeps=cfg.n_substeps, mesh_map=g.mesh_map, phys=self.phys, device=dev)
+            self.eef_pose = np.zeros((E, 3), np.float32)
         # Gaussians: per-env sets generated on the device from per-env seeds
         P = cfg.P
         n_obj = int(P * cfg.obj_frac)
@@ -171,6 +178,22 @@ class BatchedEnv:
         self.finger_pose = self.finger_pose + vel * np.float32(self.dt * ns)
         return pts, ctr, dyn_vel, dyn_omega
 
+    def make_commands(self, frame: int):
+        """Seeded per-env end-effector commands for this frame, as PhysTwinDynamics.step hands them to the
+        dynamics module (phystwin.py:104-147): eef_xyz (E,3), eef_vel (E,3), eef_rot (E,3,3), eef_rot_vel (E,3),
+        gripper_openness (E,) -- 19 floats per environment instead of the (S,48,3) vertex tables."""
+        cfg, E = self.cfg, self.cfg.E
+        rng = np.random.default_rng(cfg.seed + 1000 * frame + cfg.env_offset)
+        vel = rng.uniform(-0.1, 0.1, (E, 3)).astype(np.float32)
+        vel[:, 2] = rng.uniform(-0.05, 0.02, E)
+        rot_vel = rng.normal(0.0, 0.2, (E, 3)).astype(np.float32)
+        phase = np.random.default_rng(cfg.seed + 3).uniform(0, 6.28, E + cfg.env_offset)[cfg.env_offset:]
+        openness = (0.3 + 0.12 * np.sin(phase + 0.25 * frame)).astype(np.float32)   # gap 2.1 .. 3.8 cm
+        xyz = (self.eef_init[None] + self.eef_pose).astype(np.float32)
+        rot = np.repeat(synth.EEF_ROT_DOWN[None], E, 0).astype(np.float32)
+        self.eef_pose = self.eef_pose + vel * np.float32(self.dt * cfg.n_substeps)
+        return xyz, vel, rot, rot_vel, openness
+
     def make_link_poses(self, frame: int) -> np.ndarray:
         """(E, L, 4, 4) float32 FK poses of every env's robot links for this frame: each joint of the chain
         swings smoothly about its rest frame (stand-in for sapien FK of the policy's qpos,
@@ -190,9 +213,11 @@ class BatchedEnv:
             out[:, s] = cur
         return out.astype(np.float32)
 
-    def step(self, motion=None, out=None, link_pose=None):
-        """One frame for every env: [gripper tables ->] collision graph -> substeps -> LBS -> robot links -> render.
-        `motion`: device tensors (interp_pts, interp_center, dyn_vel, dyn_omega) or None.
+    def step(self, motion=None, out=None, link_pose=None, command=None):
+        """One frame for every env: [end-effector step ->] collision graph -> substeps -> LBS -> robot links -> render.
+        `command`: device tensors (eef_xyz, eef_vel, eef_rot, eef_rot_vel, gripper_openness) -- the per-substep
+        tables and the grasp hysteresis are then made on the device (r2s_eef_forward); or
+        `motion`: ready-made device tables (interp_pts, interp_center, dyn_vel, dyn_omega); or neither.
         `link_pose`: [E,L,4,4] device tensor of the robot's FK link poses for this frame, or None (robot kept).
         `out`: optional (color, depth[, rgb8]) device tensors to render into (double buffering); rgb8 is
         the [B,H,W,3] uint8 image the reference's evaluation loop builds on the host
@@ -201,7 +226,9 @@ class BatchedEnv:
         rgb8 = out[2] if out is not None and len(out) > 2 else None
         if self.phys.self_collision:
             self.phys.update_collision_graph()       # once per frame (phystwin.py:365-366)
-        if motion is not None:
+        if command is not None:
+            self.eef.forward(*command)               # reads last frame's collision_forces, fills the tables in place
+        elif motion is not None:
             self.phys.set_mesh_motion(*motion)
         self.x_prev4.copy_(self.phys.x4)             # state['x'] before the frame (gs_renderer.py:727)
         self.phys.step()

@@ -222,6 +222,21 @@ class BatchedSpringMass:
                                                          _ptr(dyn_omega), per_env, _stream(dev)), "set_mesh_motion")
         self._keep_motion = (interp_pts, interp_center, dyn_vel, dyn_omega)
 
+    def motion_tables(self, per_env: bool = True):
+        """Zero-copy views of the handle's own motion tables (r2s_phys_motion_ptrs): interp_pts
+        [(E,) S, n_dyn, 3], interp_center [(E,) S, 3], dyn_vel [(E,) 2, 3], dyn_omega [(E,) 1, 3] -- what a
+        device-side producer (r2s_eef_forward) fills in place of set_mesh_motion."""
+        m = _lib.PhysMotion()
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize(self.device)   # switching per_env re-allocates
+            _lib.check(self.lib.r2s_phys_motion_ptrs(self.h, int(per_env), C.byref(m)), "r2s_phys_motion_ptrs")
+        lead = (m.n_env,) if per_env else ()
+        dev = self.device
+        return (_view(m.interp_pts, lead + (m.n_substeps, m.n_dyn_verts, 3), torch.float32, dev),
+                _view(m.interp_center, lead + (m.n_substeps, 3), torch.float32, dev),
+                _view(m.dyn_vel, lead + (m.dyn_vel_rows, 3), torch.float32, dev),
+                _view(m.dyn_omega, lead + (1, 3), torch.float32, dev))
+
     # ---- collisions + stepping
     def create_resting_case(self):
         with torch.cuda.device(self.device):

@@ -272,6 +272,17 @@ def make_gripper(center, gap=0.03) -> Gripper:
     return Gripper(verts, faces, mesh_map, np.arange(len(faces), dtype=np.int32))
 
 
+EEF_ROT_DOWN = np.diag([1.0, -1.0, -1.0]).astype(np.float32)   # gripper frame = world with y, z flipped (phystwin.py:423-428)
+
+
+def gripper_opening_table(center, gap_closed=0.008, gap_open=0.08, n=101) -> np.ndarray:
+    """(n, 48, 3) float32: the finger vertices at opening k/(n-1), at the initial end-effector pose -- the
+    samples `eef_pts_list` the reference builds by IK + FK at setup (robot_pc_transformations.py:183-189)
+    and interpolates with scipy interp1d.  Opening 0 = closed (gap_closed), 1 = open (gap_open)."""
+    return np.stack([make_gripper(center, gap_closed + (gap_open - gap_closed) * k / (n - 1)).verts
+                     for k in range(n)]).astype(np.float32)
+
+
 def gripper_motion(g: Gripper, n_substeps: int, dt: float, eef_vel, close_speed=0.0, omega=(0, 0, 0)):
     """Per-substep tables in the layout SpringMassSystemWarp.set_mesh_interactive takes
     (spring_mass_warp.py:769-804; produced by phystwin.py:374-460 in the reference):

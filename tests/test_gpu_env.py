@@ -62,3 +62,41 @@ def test_tblock_1024_envs_physics_only():
     o = _util.oracle_from_scene(sc, 10)
     o.update_collision_graph(); o.step()
     assert np.abs(x[517].cpu().numpy() - o.x).max() <= 2e-6
+
+
+def test_command_driven_env_closed_loop_matches_the_oracles():
+    """N3 in the loop: the env is driven by end-effector COMMANDS (19 floats per env and frame); vertex tables and
+    the grasp hysteresis are made on the device from last frame's finger forces.  The CPU side closes the same
+    loop with oracle/eef_ref.py + oracle/physics_ref.c."""
+    import torch
+    import r2s_testutil as util
+    from oracle import eef_ref
+    from real2sim_eval_b200 import synth
+    from real2sim_eval_b200.envs import BatchedEnv, EnvBatchConfig
+    cfg = EnvBatchConfig(scene="rope", E=3, W=64, H=64, cameras=1, n_substeps=10, P=3000)
+    env = BatchedEnv(cfg, "cuda")
+    e = 1
+    x0, v0 = env.phys.get_state()
+    sc = synth.pose_scene(env.base, cfg.seed + e)
+    o = util.oracle_from_scene(sc, cfg.n_substeps, mesh=util.gripper_mesh_dict(env.gripper))
+    assert np.array_equal(o.x, x0[e].cpu().numpy())
+    o.create_resting_case() if env.phys.self_collision else None
+    table = env.eef.table.cpu().numpy()
+    faces = eef_ref.force_faces(env.gripper.mesh_map)
+    cur, grasped = None, False
+    for f in range(3):
+        cmd = env.make_commands(f)
+        env.step(command=tuple(torch.tensor(a).cuda().contiguous() for a in cmd))
+        xyz, vel, rot, rvel, opn = (a[e] for a in cmd)
+        r = eef_ref.eef_step(table, env.eef_init, xyz, vel, rot, rvel, opn, dt=env.dt, n_substeps=cfg.n_substeps,
+                             current_openness=cur, grasped=grasped, forces=o.collision_forces, faces=faces)
+        cur, grasped = r["current_openness"], r["grasped"]
+        o.set_mesh_interactive(r["interp_pts"], r["interp_center"], r["dyn_vel"], r["dyn_omega"])
+        if env.phys.self_collision:
+            o.update_collision_graph()
+        o.step()
+        assert float(env.eef.current_openness[e]) == cur and bool(env.eef.grasped[e]) == grasped
+        x = env.phys.get_state()[0][e].cpu().numpy()
+        off = np.abs(x - o.x).max(1) > 1e-5
+        assert off.mean() <= 0.01, f"frame {f}: {off.sum()} particles beyond 1e-5 m"   # contact ties, see DESIGN.md §2
+    assert torch.isfinite(env.color).all()

@@ -144,7 +144,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     W, H = args.res
     cfg = EnvBatchConfig(scene=args.scene, E=args.envs, W=W, H=H, cameras=args.cameras, n_substeps=args.substeps,
-                         P=args.gaussians, env_offset=shard_envs(world * args.envs, world, rank).start)
+                         P=args.gaussians, env_offset=shard_envs(world * args.envs, world, rank).start,
+                         success_start_frame=0)
     env = BatchedEnv(cfg, dev)
     lib = _lib.load()
     E, ns = cfg.E, cfg.n_substeps
@@ -189,6 +190,7 @@ def run_ours(args):
     pe2 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     pe3 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     pem = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    pes = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     import ctypes
     prof = (ctypes.c_float * 5)()
     ev0.record()
@@ -203,6 +205,8 @@ def run_ours(args):
         pe0[k].record()
         env.phys.step()
         pe1[k].record()
+        env.success.update(env.phys.x4)
+        pes[k].record()
         env.lbs.forward(env.x_prev4, env.phys.x4, env.means3D)
         pe2[k].record()
         env.links.forward(m[5], env.means3D, env.rotations)
@@ -219,7 +223,8 @@ def run_ours(args):
     _lib.check(lib.r2s_raster_get_profile(prof), "get_profile")   # stages of the LAST timed step
     stage_ms = np.array(list(prof), dtype=np.float64)
     phys_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe0, pe1)]))
-    lbs_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe1, pe2)]))
+    succ_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe1, pes)]))
+    lbs_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pes, pe2)]))
     links_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pe2, pe3)]))
     eef_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pem, pe0)]))   # incl. the x_prev copy
     lib.r2s_raster_set_profile(0)
@@ -324,7 +329,8 @@ def run_ours(args):
     # ---- metrics all-gather (the only collective)
     cx = float(env.phys.x.double().sum())
     crgb = float(env.color.double().sum())
-    gathered = shard.gather_metrics([args.steps, ms_total / 1e3, cx, crgb], dev)
+    succ, hits = env.success.result()
+    gathered = shard.gather_metrics([args.steps, ms_total / 1e3, cx, crgb, float(succ.sum()), float(hits.sum())], dev)
 
     # ---- roofline of the dominant kernel (algorithmic bytes: SURVEY.md §8d)
     pk, pk_kind = peaks()
@@ -340,7 +346,8 @@ def run_ours(args):
         "composite": R * 40 + B * W * H * 16,
     }
     alg["eef"] = E * (19 * 4 + ns * (env.eef.V + 1) * 12 + 36 + env.eef.V * 24)   # command in, tables out (+ 2 table rows)
-    times = {"eef": eef_ms, "phys_frame": phys_ms, "lbs": lbs_ms, "links": links_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
+    alg["success"] = E * (env.base.N * 16 + (env.base.S * 8 if cfg.scene == "rope" else 0) + 24)
+    times = {"eef": eef_ms, "phys_frame": phys_ms, "success": succ_ms, "lbs": lbs_ms, "links": links_ms, "preprocess": stage_ms[0], "scan": stage_ms[1], "emit": stage_ms[2],
              "tile_sort": stage_ms[3], "composite": stage_ms[4]}
     dom = max(alg, key=lambda k: times[k])   # dominant kernel among those with an algorithmic-byte model
     ach = alg[dom] / (times[dom] / 1e3) / 1e9
@@ -371,7 +378,7 @@ def run_ours(args):
                    "mean_tile_list": round(R / (B * T), 1), "parallelism": f"env-shard x{world}",
                    "l2_policy": "inputs larger than L2 (2.9 GB of Gaussians + 1.07 GB of images per step)"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-        "metrics_allgather": {"per_rank": gathered, "fields": ["steps", "seconds", "checksum_x", "checksum_rgb"]},
+        "metrics_allgather": {"per_rank": gathered, "fields": ["steps", "seconds", "checksum_x", "checksum_rgb", "episodes_succeeded", "frames_passed"]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # timed on rank 0 at N=1 only
         line["cpu_baseline"] = cpu_baseline(args, env)

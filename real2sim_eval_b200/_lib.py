@@ -72,6 +72,16 @@ class EefArgs(C.Structure):  # include/r2s_eef.h: r2s_eef_args
     ]
 
 
+class SuccessArgs(C.Structure):  # include/r2s_metrics.h: r2s_success_args
+    _fields_ = [
+        ("E", c_i32), ("N", c_i32), ("S", c_i32), ("task", c_i32), ("frame", c_i32), ("start_frame", c_i32),
+        ("need_frames", c_i32), ("ring_slots", c_i32),
+        ("x4", c_vp), ("shift", c_vp), ("target", c_vp), ("springs", c_vp),
+        ("box", C.c_double * 15), ("threshold", C.c_double),
+        ("value", c_vp), ("passed", c_vp), ("hits", c_vp), ("success", c_vp), ("ring", c_vp),
+    ]
+
+
 class PhysMotion(C.Structure):  # include/r2s_phys.h: r2s_phys_motion
     _fields_ = [
         ("interp_pts", c_vp), ("interp_center", c_vp), ("dyn_vel", c_vp), ("dyn_omega", c_vp),
@@ -124,6 +134,7 @@ SYMBOLS = [
     ("r2s_lbs_forward", C.c_int, [C.POINTER(LbsArgs), c_vp]),
     ("r2s_links_forward", C.c_int, [C.POINTER(LinksArgs), c_vp]),
     ("r2s_eef_forward", C.c_int, [C.POINTER(EefArgs), c_vp]),
+    ("r2s_success_forward", C.c_int, [C.POINTER(SuccessArgs), c_vp]),
 ]
 
 _lib = None

@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libr2s.so")
-SOURCES = ["common.cu", "phys.cu", "raster.cu", "lbs.cu", "links.cu", "eef.cu"]
+SOURCES = ["common.cu", "phys.cu", "raster.cu", "lbs.cu", "links.cu", "eef.cu", "metrics.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -20,6 +20,7 @@ import torch
 from . import _lib, synth
 from .eef import BatchedEefMotion
 from .lbs import BatchedLBS
+from .metrics import BatchedSuccess
 from .links import BatchedLinkTransform
 from .physics import BatchedSpringMass
 from .rasterizer import BatchedRasterizer
@@ -45,6 +46,8 @@ class EnvBatchConfig:
     seed: int = 1234
     env_offset: int = 0          # global index of this shard's first env (multi-GPU sharding)
     gripper: bool = True
+    success_start_frame: int | None = None   # None: the task's own (1700 / 800 / 350); frames before it do not count
+    state_ring: int = 0          # frames of packed particle positions kept on the device (0 = none)
     instances_per_gaussian: float = 8.0
 
 
@@ -79,6 +82,16 @@ class BatchedEnv:
         if self.phys.self_collision:
             self.phys.create_resting_case()
         self.dt = pr["dt"]
+        # N4: per-frame task-success test + episode counters on the device (calculate_success_{T,rope,sloth}.py)
+        task = {"rope": "rope", "sloth": "sloth", "tblock": "pusht"}[cfg.scene]
+        kw = dict(start_frame=cfg.success_start_frame, ring_slots=cfg.state_ring, device=dev)
+        if task == "rope":
+            self.success = BatchedSuccess(task, E, base.N, springs=base.springs, **kw)
+        elif task == "pusht":
+            self.success = BatchedSuccess(task, E, base.N, target=base.x, **kw)
+        else:   # container box of the packing task: 0.2 x 0.13 x 0.27 m, enlarged by 1.05 (calculate_success_sloth.py:155-158)
+            obb = (np.array([0.0, 0.0, 0.135]), np.eye(3), np.array([0.2, 0.13, 0.27]) * 1.05)
+            self.success = BatchedSuccess(task, E, base.N, obb=obb, **kw)
         # gripper: two fingers straddling the object near its centre, per-env motion tables
         self.gripper = None
         if cfg.gripper:
@@ -232,6 +245,7 @@ class BatchedEnv:
             self.phys.set_mesh_motion(*motion)
         self.x_prev4.copy_(self.phys.x4)             # state['x'] before the frame (gs_renderer.py:727)
         self.phys.step()
+        self.success.update(self.phys.x4)            # task test + episode counters (+ state ring) for this frame
         self.lbs.forward(self.x_prev4, self.phys.x4, self.means3D)
         if self.links is not None and link_pose is not None:   # robot Gaussians follow this frame's FK poses
             self.links.forward(link_pose, self.means3D, self.rotations)

@@ -38,16 +38,17 @@ def test_ctypes_struct_mirrors_match_the_c_headers(tmp_path):
     from real2sim_eval_b200 import _lib
     src = tmp_path / "sz.c"
     src.write_text('#include <stdio.h>\n#include "r2s_phys.h"\n#include "r2s_raster.h"\n#include "r2s_lbs.h"\n'
-                   '#include "r2s_links.h"\n#include "r2s_eef.h"\n'
-                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(r2s_phys_desc), sizeof(r2s_phys_ptrs),'
+                   '#include "r2s_links.h"\n#include "r2s_eef.h"\n#include "r2s_metrics.h"\n'
+                   'int main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(r2s_phys_desc), sizeof(r2s_phys_ptrs),'
                    ' sizeof(r2s_raster_args), sizeof(r2s_raster_layout), sizeof(r2s_lbs_args), sizeof(r2s_links_args),'
-                   ' sizeof(r2s_eef_args), sizeof(r2s_phys_motion)); return 0;}\n')
+                   ' sizeof(r2s_eef_args), sizeof(r2s_phys_motion), sizeof(r2s_success_args)); return 0;}\n')
     exe = tmp_path / "sz"
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
     subprocess.run([cc, "-I", INC, str(src), "-o", str(exe)], check=True)   # the headers are plain C
     got = list(map(int, subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()))
     want = [C.sizeof(_lib.PhysDesc), C.sizeof(_lib.PhysPtrs), C.sizeof(_lib.RasterArgs), C.sizeof(_lib.RasterLayout),
-            C.sizeof(_lib.LbsArgs), C.sizeof(_lib.LinksArgs), C.sizeof(_lib.EefArgs), C.sizeof(_lib.PhysMotion)]
+            C.sizeof(_lib.LbsArgs), C.sizeof(_lib.LinksArgs), C.sizeof(_lib.EefArgs), C.sizeof(_lib.PhysMotion),
+            C.sizeof(_lib.SuccessArgs)]
     assert got == want
 
 
@@ -66,6 +67,7 @@ def test_argument_validation_reports_through_last_error():
     assert lib.r2s_raster_get_profile(None) == -1
     assert lib.r2s_lbs_forward(None, None) == -1 and b"null args" in lib.r2s_last_error()
     assert lib.r2s_eef_forward(None, None) == -1 and b"null args" in lib.r2s_last_error()
+    assert lib.r2s_success_forward(None, None) == -1 and b"null args" in lib.r2s_last_error()
     e = _lib.EefArgs()
     e.E, e.n_substeps, e.n_pts, e.n_table = 1, 4096, 48, 101
     assert lib.r2s_eef_forward(C.byref(e), None) == -1 and b"bad sizes" in lib.r2s_last_error()

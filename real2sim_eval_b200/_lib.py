@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libr2s.so")
+LIB_PATH = os.environ.get("R2S_LIB", os.path.join(_HERE, "libr2s.so"))
 
 c_i32, c_i64, c_f, c_vp, c_sz = C.c_int32, C.c_int64, C.c_float, C.c_void_p, C.c_size_t
 

@@ -50,6 +50,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         common += ["-ccbin", host_cc]
     if verbose:
         common += ["-Xptxas", "-v"]
+    common += os.environ.get("R2S_NVCC_FLAGS", "").split()
+    out = os.environ.get("R2S_LIB_OUT", OUT)
     procs = []
     for src in SOURCES:
         obj = os.path.join(bdir, src.replace(".cu", ".o"))
@@ -58,8 +60,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     for pr in procs:
         if pr.wait() != 0:
             raise RuntimeError("nvcc failed building libr2s.so")
-    subprocess.run(common + ["-shared", *objs, "-o", OUT], check=True)
-    return OUT
+    subprocess.run(common + ["-shared", *objs, "-o", out], check=True)
+    return out
 
 
 if __name__ == "__main__":

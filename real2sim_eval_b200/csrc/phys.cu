@@ -74,6 +74,7 @@ struct FrameParams {
     const int* faces;         // [F][3]
     const int* mesh_map;      // [F]
     const int* face_map;      // [F]
+    const int* dyn_part;      // [n_dyn] part (0..kMaxParts-1) of each dynamic vertex: one bounding box per part
     const float* interp_pts;  // [(E)][n_sub_table][n_dyn][3]
     long long interp_stride;  // per env (0 = shared)
     const float* interp_center;  // [(E)][n_sub_table][3]
@@ -322,6 +323,9 @@ __device__ __forceinline__ float3 mesh_eval(const MeshView& m, int face, float u
 // kPrecise: IEEE sqrt / divisions in the reference's expression order (SMW:87-99).
 // !kPrecise: one rsqrt + Newton step gives 1/len, the rest length is stored as its reciprocal;
 // same formula, ~4x fewer instructions per spring, results within a few ulp of the precise path.
+constexpr int kMaxParts = 4;                               // separately boxed parts of the dynamic mesh
+constexpr float kBoxGrow = 0.005f * 1.0001f + 1e-6f;       // the largest contact margin (+ slack)
+
 template <int G, bool kSmemState, bool kPrecise, bool kAccel>
 __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
 {
@@ -339,8 +343,9 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
     float* const svb = kSmemState ? reinterpret_cast<float*>(smem4 + 2 * N) : p.vb_scratch + (size_t)e * 3 * N;  // [3][N]
     unsigned char* sp = reinterpret_cast<unsigned char*>(smem4) +
                         (kSmemState ? sizeof(float4) * 2 * N + sizeof(float) * 3 * Npad : 0);
-    float* s_aabb = reinterpret_cast<float*>(sp); sp += sizeof(float) * 16;  // [0..5] dyn, [6..11] static
-    int* s_ncand = reinterpret_cast<int*>(s_aabb + 12);                      // candidates of this substep
+    // boxes: kMaxParts parts of the dynamic mesh (one per finger / tool) at [6k..6k+5], static vertices at [24..29]
+    float* s_aabb = reinterpret_cast<float*>(sp); sp += sizeof(float) * 32;
+    int* s_ncand = reinterpret_cast<int*>(s_aabb + 30);                      // candidates of this substep
     float* s_rigid = reinterpret_cast<float*>(sp); sp += sizeof(float) * 16; // world = R rest + t of this substep (accel)
     int* s_cand = reinterpret_cast<int*>(sp);                                // particles near the mesh
     if (p.F > 0) sp += sizeof(int) * ((N + 3) & ~3);
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                 hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
             }
         if (tid == 0)
-            for (int c = 0; c < 3; ++c) { s_aabb[6 + c] = lo[c]; s_aabb[9 + c] = hi[c]; }
+            for (int c = 0; c < 3; ++c) { s_aabb[24 + c] = lo[c]; s_aabb[27 + c] = hi[c]; }
     }
     const bool run_B = p.has_self_collision && p.status[4 * e] > 0;
     const float* rest = p.rest + (size_t)e * p.rest_stride;
@@ -430,25 +435,29 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         for (int c = 0; c < 3; ++c) { lo[c] = fminf(lo[c], w[c]); hi[c] = fmaxf(hi[c], w[c]); }
                     }
                     for (int c = 0; c < 3; ++c) { s_aabb[c] = lo[c]; s_aabb[3 + c] = hi[c]; }
+                    for (int k = 1; k < kMaxParts; ++k)
+                        for (int c = 0; c < 3; ++c) { s_aabb[6 * k + c] = 3e38f; s_aabb[6 * k + 3 + c] = -3e38f; }
                     *s_ncand = 0;
                 }
-            } else if (tid < 32) {  // SMW:889-899 set_mesh_points + refit (bounds)
+            } else if (tid < 32 * kMaxParts) {  // SMW:889-899 set_mesh_points + refit (bounds): warp w = part w
+                const int part = tid >> 5, ln = tid & 31;
                 float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
-                for (int k = tid; k < p.n_dyn; k += 32)
+                for (int k = ln; k < p.n_dyn; k += 32) {
+                    if (p.dyn_part[k] != part) continue;
                     for (int c = 0; c < 3; ++c) {
                         float q = row[3 * k + c];
                         if (p.stage_dyn) s_dyn[3 * k + c] = q;
                         lo[c] = fminf(lo[c], q); hi[c] = fmaxf(hi[c], q);
                     }
+                }
                 for (int c = 0; c < 3; ++c)
                     for (int o = 16; o > 0; o >>= 1) {
                         lo[c] = fminf(lo[c], __shfl_xor_sync(kFull, lo[c], o));
                         hi[c] = fmaxf(hi[c], __shfl_xor_sync(kFull, hi[c], o));
                     }
-                if (tid == 0) {
-                    for (int c = 0; c < 3; ++c) { s_aabb[c] = lo[c]; s_aabb[3 + c] = hi[c]; }
-                    *s_ncand = 0;
-                }
+                if (ln == 0)
+                    for (int c = 0; c < 3; ++c) { s_aabb[6 * part + c] = lo[c]; s_aabb[6 * part + 3 + c] = hi[c]; }
+                if (tid == 0) *s_ncand = 0;
             }
         }
         // ============ phase A: spring forces (gather) + velocity update -> svb
@@ -571,11 +580,16 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
             // closer than `margin` (5 mm fingers, 1 mm otherwise) to its surface: a hit between margin and
             // max_dist = 20 mm has err >= 0 and leaves v unchanged and x advanced, exactly like no hit
             // (SMW:349-351, 415-421), so those particles need no query at all.
-            const float grow = 0.005f * 1.0001f + 1e-6f;
-            box_lo = f3(fminf(s_aabb[0], s_aabb[6]) - grow, fminf(s_aabb[1], s_aabb[7]) - grow,
-                        fminf(s_aabb[2], s_aabb[8]) - grow);
-            box_hi = f3(fmaxf(s_aabb[3], s_aabb[9]) + grow, fmaxf(s_aabb[4], s_aabb[10]) + grow,
-                        fmaxf(s_aabb[5], s_aabb[11]) + grow);
+            // The test is made per part of the mesh (each finger / the tool / the static vertices has its own
+            // box): between two open fingers nothing is queued until a finger comes within the margin.
+            box_lo = f3(3e38f, 3e38f, 3e38f);
+            box_hi = f3(-3e38f, -3e38f, -3e38f);
+            for (int k = 0; k <= kMaxParts; ++k) {
+                box_lo = f3(fminf(box_lo.x, s_aabb[6 * k]), fminf(box_lo.y, s_aabb[6 * k + 1]), fminf(box_lo.z, s_aabb[6 * k + 2]));
+                box_hi = f3(fmaxf(box_hi.x, s_aabb[6 * k + 3]), fmaxf(box_hi.y, s_aabb[6 * k + 4]), fmaxf(box_hi.z, s_aabb[6 * k + 5]));
+            }
+            box_lo = box_lo - f3(kBoxGrow, kBoxGrow, kBoxGrow);
+            box_hi = box_hi + f3(kBoxGrow, kBoxGrow, kBoxGrow);
             c0 = f3(g_center[3 * step], g_center[3 * step + 1], g_center[3 * step + 2]);
             omega = f3(g_omega[0], g_omega[1], g_omega[2]);
             dv0 = f3(g_dynvel[0], g_dynvel[1], g_dynvel[2]);
@@ -612,8 +626,17 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
             const float3 v0 = run_B ? xyz(sv[i]) : f3(svb[i], svb[N + i], svb[2 * N + i]);
             if (has_mesh) {
                 const float3 next_x = x0 + v0 * dt;
-                const bool near_box = next_x.x >= box_lo.x && next_x.x <= box_hi.x && next_x.y >= box_lo.y &&
-                                      next_x.y <= box_hi.y && next_x.z >= box_lo.z && next_x.z <= box_hi.z;
+                bool near_box = next_x.x >= box_lo.x && next_x.x <= box_hi.x && next_x.y >= box_lo.y &&
+                                next_x.y <= box_hi.y && next_x.z >= box_lo.z && next_x.z <= box_hi.z;
+                if (near_box) {   // inside the union box: test the parts
+                    near_box = false;
+                    for (int k = 0; k <= kMaxParts; ++k) {
+                        const float* b = s_aabb + 6 * k;
+                        near_box = near_box || (next_x.x >= b[0] - kBoxGrow && next_x.x <= b[3] + kBoxGrow &&
+                                                next_x.y >= b[1] - kBoxGrow && next_x.y <= b[4] + kBoxGrow &&
+                                                next_x.z >= b[2] - kBoxGrow && next_x.z <= b[5] + kBoxGrow);
+                    }
+                }
                 if (near_box) {
                     s_cand[atomicAdd(s_ncand, 1)] = i;
                     if (!run_B) sv[i] = make_float4(v0.x, v0.y, v0.z, 0.0f);  // C2 reads v_before_ground from sv
@@ -943,6 +966,7 @@ struct r2s_phys {
     int* faces = nullptr;
     int* mesh_map = nullptr;
     int* face_map = nullptr;
+    int* dyn_part = nullptr;
     float* coll_forces = nullptr;
     float* interp_pts = nullptr;
     float* interp_center = nullptr;
@@ -982,7 +1006,7 @@ int dmalloc(T** p, size_t n)
 int configure_launch(r2s_phys* h)
 {
     const int N = h->d.N;
-    size_t misc = sizeof(float) * 32;   // bounding boxes + rigid transform
+    size_t misc = sizeof(float) * 48;   // bounding boxes + rigid transform
     h->stage_dyn = 0;
     h->smem_forces = 0;
     if (h->F > 0) {
@@ -1257,7 +1281,7 @@ int r2s_phys_destroy(r2s_phys* h)
     if (!h) return R2S_OK;
     void* ptrs[] = {h->row_ptr, h->nbr, h->sid, h->nbr_k, h->rest_csr, h->logY, h->mass, h->mask, h->x4, h->v4,
                     h->vb_scratch, h->coll_num, h->coll_idx, h->status, h->resting, h->key_scratch,
-                    h->stat_verts, h->faces, h->mesh_map, h->face_map, h->coll_forces, h->interp_pts,
+                    h->stat_verts, h->faces, h->mesh_map, h->face_map, h->dyn_part, h->coll_forces, h->interp_pts,
                     h->interp_center, h->dyn_vel, h->dyn_omega, h->frec, h->vnorm, h->cell_start, h->cell_tris};
     for (void* p : ptrs)
         if (p) cudaFree(p);
@@ -1341,7 +1365,7 @@ int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, con
         R2S_REQUIRE(faces[k] >= 0 && faces[k] < V, "r2s_phys_set_mesh: face index out of range");
     for (int k = 0; k < F; ++k)
         R2S_REQUIRE(face_map[k] >= 0 && face_map[k] < F, "r2s_phys_set_mesh: face_map out of range");
-    void* old[] = {h->stat_verts, h->faces, h->mesh_map, h->face_map, h->coll_forces, h->interp_pts,
+    void* old[] = {h->stat_verts, h->faces, h->mesh_map, h->face_map, h->dyn_part, h->coll_forces, h->interp_pts,
                    h->interp_center, h->dyn_vel, h->dyn_omega};
     for (void* p : old)
         if (p) cudaFree(p);
@@ -1359,6 +1383,22 @@ int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, con
     R2S_CUDA_TRY(cudaMemcpy(h->mesh_map, mesh_map, sizeof(int) * F, cudaMemcpyHostToDevice));
     R2S_CUDA_TRY(cudaMemcpy(h->face_map, face_map, sizeof(int) * F, cudaMemcpyHostToDevice));
     R2S_CUDA_TRY(cudaMemset(h->coll_forces, 0, sizeof(float) * (size_t)E * F * 3));
+    {   // one broad-phase box per dynamic mesh (finger / tool): part = rank of the mesh_map value of a face that
+        // uses the vertex, among the distinct values on dynamic faces; more than four meshes share the last box
+        std::vector<int> part(n_dyn > 0 ? n_dyn : 1, 0), ids;
+        for (int f = 0; f < F; ++f)
+            for (int c = 0; c < 3; ++c) {
+                const int v = faces[3 * f + c];
+                if (v >= n_dyn) continue;
+                int k = 0;
+                while (k < (int)ids.size() && ids[k] != mesh_map[f]) ++k;
+                if (k == (int)ids.size()) ids.push_back(mesh_map[f]);
+                part[v] = k < 4 ? k : 3;
+            }
+        h->dyn_part = nullptr;
+        if (dmalloc(&h->dyn_part, part.size())) return R2S_ERR_CUDA;
+        R2S_CUDA_TRY(cudaMemcpy(h->dyn_part, part.data(), sizeof(int) * part.size(), cudaMemcpyHostToDevice));
+    }
     // SMW:699-711 defaults: rest pose repeated over the substeps, centre = mean, zero velocities
     std::vector<float> tbl((size_t)ns * n_dyn * 3 + 1), ctr((size_t)ns * 3 + 1), zero(6, 0.f);
     double c[3] = {0, 0, 0};
@@ -1489,7 +1529,7 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     p.rest_stride = h->rest_envs > 1 ? h->nd : 0;
     p.mass = h->mass; p.mask = h->mask; p.x4 = h->x4; p.v4 = h->v4; p.vb_scratch = h->vb_scratch;
     p.coll_num = h->coll_num; p.coll_idx = h->coll_idx; p.status = h->status;
-    p.stat_verts = h->stat_verts; p.faces = h->faces; p.mesh_map = h->mesh_map; p.face_map = h->face_map;
+    p.stat_verts = h->stat_verts; p.faces = h->faces; p.mesh_map = h->mesh_map; p.face_map = h->face_map; p.dyn_part = h->dyn_part;
     p.interp_pts = h->interp_pts; p.interp_center = h->interp_center; p.dyn_vel = h->dyn_vel; p.dyn_omega = h->dyn_omega;
     const long long pe = h->motion_per_env ? 1 : 0;
     p.interp_stride = pe * h->d.n_substeps * h->n_dyn * 3;

@@ -798,6 +798,107 @@ __global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
     }
     if (!kResting && tid == 0) { p.status[4 * e] = 0; p.status[4 * e + 1] = 0; }
     __syncthreads();
+    // ---- cell sort.  Fast path: when the occupied cells span a box of at most N cells (<= 128 per axis), a
+    // counting sort on the box-local (z, y, x) cell rank gives exactly the order of the Warp
+    // cell id (ascending id inside a cell): histogram, scan, unordered scatter, then each entry finds its rank
+    // inside its cell by counting the smaller ids there -- 6 barriers instead of the bitonic network's
+    // log2(n)(log2(n)+1)/2.  Otherwise (huge or wrapping extents): bitonic sort of the (cell, id) keys.
+    __shared__ int s_lo[3], s_hi[3], s_c0[3], s_fast;
+    if (tid < 3) { s_lo[tid] = 0x7fffffff; s_hi[tid] = -0x7fffffff; }
+    __syncthreads();
+    {
+        int lo3[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi3[3] = {-0x7fffffff, -0x7fffffff, -0x7fffffff};
+        for (int i = tid; i < N; i += nt) {
+            const float4 q = x4[i];
+            const int c3[3] = {(int)(q.x * inv_w), (int)(q.y * inv_w), (int)(q.z * inv_w)};
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo3[a] = min(lo3[a], c3[a]); hi3[a] = max(hi3[a], c3[a]); }
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            for (int o = 16; o > 0; o >>= 1) {
+                lo3[a] = min(lo3[a], __shfl_xor_sync(0xffffffffu, lo3[a], o));
+                hi3[a] = max(hi3[a], __shfl_xor_sync(0xffffffffu, hi3[a], o));
+            }
+            if ((tid & 31) == 0) { atomicMin(&s_lo[a], lo3[a]); atomicMax(&s_hi[a], hi3[a]); }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const long long ex = (long long)s_hi[0] - s_lo[0] + 1, ey = (long long)s_hi[1] - s_lo[1] + 1,
+                        ez = (long long)s_hi[2] - s_lo[2] + 1;
+        const int origin = 1 << 20;
+        bool ok = p.stage_x && !p.key_scratch && ex * ey * ez <= (long long)N && ex <= R2S_GRID_DIM &&
+                  ey <= R2S_GRID_DIM && ez <= R2S_GRID_DIM;
+        // Per axis the hashed coordinate (c + 2^20) % 128 orders the box's cells; it wraps at most once inside a
+        // box of <= 128 cells, at c0 = the first coordinate whose hash is 0: cells c >= c0 come first.
+        // s_c0[a] = c0 when lo < c0 <= hi, else lo (no wrap).  Shifted coordinates must be non-negative
+        // (grid_cell clamps at 0).
+        for (int a = 0; a < 3 && ok; ++a) {
+            ok = s_lo[a] + origin >= 0;
+            const int c0 = (s_lo[a] + origin + R2S_GRID_DIM - 1) / R2S_GRID_DIM * R2S_GRID_DIM - origin;
+            s_c0[a] = (c0 > s_lo[a] && c0 <= s_hi[a]) ? c0 : s_lo[a];
+        }
+        s_fast = ok ? 1 : 0;
+    }
+    __syncthreads();
+    if (s_fast) {
+        // scratch in the region that holds the cell-sorted positions afterwards (16 B per particle):
+        // cnt[nc] | start[nc] | tmp_id[N] | cidx[N]  with nc <= N
+        const int ex = s_hi[0] - s_lo[0] + 1, ey = s_hi[1] - s_lo[1] + 1, ez = s_hi[2] - s_lo[2] + 1;
+        const int nc = ex * ey * ez;
+        int* cnt = reinterpret_cast<int*>(smem_raw + sizeof(unsigned long long) * (size_t)p.npow2);
+        int* start = cnt + nc;
+        int* tmp_id = start + nc;
+        int* cidx = tmp_id + N;
+        __shared__ int s_wsum[32];
+        for (int c = tid; c < nc; c += nt) cnt[c] = 0;
+        __syncthreads();
+        for (int i = tid; i < N; i += nt) {
+            const float4 q = x4[i];
+            // rank of a coordinate in hash order: the part at or above the wrap point first
+            auto rank = [&](int c, int a) { return c >= s_c0[a] ? c - s_c0[a] : (s_hi[a] - s_c0[a] + 1) + (c - s_lo[a]); };
+            const int c = (rank((int)(q.z * inv_w), 2) * ey + rank((int)(q.y * inv_w), 1)) * ex + rank((int)(q.x * inv_w), 0);
+            cidx[i] = c;
+            atomicAdd(cnt + c, 1);
+        }
+        __syncthreads();
+        // exclusive scan of cnt -> start (block-wide, chunks of nt)
+        int carry = 0;
+        for (int c0 = 0; c0 < nc; c0 += nt) {
+            const int c = c0 + tid;
+            const int v = c < nc ? cnt[c] : 0;
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += u;
+            }
+            if ((tid & 31) == 31) s_wsum[tid >> 5] = incl;
+            __syncthreads();
+            int base = carry;
+            for (int w = 0; w < (tid >> 5); ++w) base += s_wsum[w];
+            if (c < nc) { start[c] = base + incl - v; cnt[c] = 0; }
+            int tot = 0;
+            for (int w = 0; w < (nt >> 5); ++w) tot += s_wsum[w];
+            carry += tot;
+            __syncthreads();
+        }
+        for (int i = tid; i < N; i += nt) {
+            const int c = cidx[i];
+            tmp_id[start[c] + atomicAdd(cnt + c, 1)] = i;
+        }
+        __syncthreads();
+        for (int t = tid; t < N; t += nt) {
+            const int i = tmp_id[t], c = cidx[i];
+            const int s0 = start[c], s1 = s0 + cnt[c];
+            int rank = 0;
+            for (int u = s0; u < s1; ++u) rank += tmp_id[u] < i;
+            const float4 q = x4[i];
+            const unsigned cell = (unsigned)grid_cell((int)(q.x * inv_w), (int)(q.y * inv_w), (int)(q.z * inv_w));
+            keys[s0 + rank] = ((unsigned long long)cell << 32) | (unsigned)i;
+        }
+        __syncthreads();
+    } else {
     for (int k = 2; k <= p.npow2; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int i = tid; i < p.npow2; i += nt) {
@@ -810,6 +911,7 @@ __global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
             }
             __syncthreads();
         }
+    }
     unsigned* resting = p.resting + (size_t)e * p.resting_stride;
     // positions in cell-sorted order next to the keys, so that walking a cell reads consecutive shared memory
     float4* sxs = reinterpret_cast<float4*>(smem_raw + sizeof(unsigned long long) * (size_t)p.npow2);
@@ -818,11 +920,20 @@ __global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
         __syncthreads();
     }
     int total = 0, overflow = 0;
+    float d2_lim = p.coll_dist * p.coll_dist;
+    while (sqrtf(d2_lim) >= p.coll_dist && d2_lim > 0.0f) d2_lim = __uint_as_float(__float_as_uint(d2_lim) - 1u);
+    while (sqrtf(d2_lim) < p.coll_dist) d2_lim = __uint_as_float(__float_as_uint(d2_lim) + 1u);
     for (int t = tid; t < N; t += nt) {
         const int i = (int)(keys[t] & 0xffffffffu);  // wp.hash_grid_point_id: cell-sorted order
         const float4 q = p.stage_x ? sxs[t] : x4[i];
         const float3 x1 = xyz(q);
-        const float r = p.radius;
+        // Warp queries the cells overlapping x +- 5*dist (the build radius) and update_potential_collision keeps
+        // a candidate only if |dx| < dist (SMW:216-225).  The cell map is monotone per axis, so every candidate
+        // that can pass lies in the cells overlapping x +- dist, and visiting only those (same x/y/z order)
+        // yields the same row in the same order; the range is widened by 1e-4 relative + 1e-6 m so that float
+        // rounding of the distance test cannot admit a point from outside it.  build_resting_collision_pairs
+        // does not filter by distance and keeps the full range.
+        const float r = kResting ? p.radius : p.coll_dist * 1.0001f + 1e-6f;
         const int xs = (int)((x1.x - r) * inv_w), ys = (int)((x1.y - r) * inv_w), zs = (int)((x1.z - r) * inv_w);
         const int xe = min((int)((x1.x + r) * inv_w), xs + R2S_GRID_DIM - 1);
         const int ye = min((int)((x1.y + r) * inv_w), ys + R2S_GRID_DIM - 1);
@@ -856,11 +967,13 @@ __global__ void __launch_bounds__(1024, 1) grid_kernel(const GridParams p)
                             // failing) distance test goes first, the resting-pair bits are fetched only for close pairs
                             if (j == i) continue;
                             const float3 dis = xyz(p.stage_x ? sxs[lo] : x4[j]) - x1;
-                            const float dis_len = len3(dis);
-                            if (!(dis_len < p.coll_dist) || mask1 == p.mask[j]) continue;
-                            const bool rest_ij = (resting[(size_t)i * p.words + (j >> 5)] >> (j & 31)) & 1u;
-                            const bool rest_ji = (resting[(size_t)j * p.words + (i >> 5)] >> (i & 31)) & 1u;
-                            if (rest_ij || rest_ji) continue;
+                            // len(dis) < dist (SMW:219) without the square root: sqrtf is monotone and correctly
+                            // rounded, so sqrtf(d2) < dist  <=>  d2 < d2_lim (the least float whose root is >= dist)
+                            if (!(dot3(dis, dis) < d2_lim) || mask1 == p.mask[j]) continue;
+                            // resting[i][j] OR resting[j][i] (SMW:216-218): the relation is only ever written
+                            // symmetrically (both bits per pair, above), so row i -- one 4*words-byte row per
+                            // particle, cache-resident across its candidates -- decides
+                            if ((resting[(size_t)i * p.words + (j >> 5)] >> (j & 31)) & 1u) continue;
                             if (cnt < p.cap) row[cnt++] = j;
                             else overflow++;
                         }

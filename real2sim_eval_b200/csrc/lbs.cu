@@ -150,44 +150,49 @@ __global__ void lbs_blend_kernel(const r2s_lbs_args a, int per_block)
         for (int k = threadIdx.x; k < 3 * a.N; k += blockDim.x) s_T[k] = Rm[k];
         __syncthreads();
     }
-    const float4* T = (kStage && use_R) ? s_T : Rm;
     const float4* b0 = reinterpret_cast<const float4*>(a.bones4) + (size_t)e * a.N;
     const float4* b1 = reinterpret_cast<const float4*>(a.bones_new4) + (size_t)e * a.N;
     const int g_end = min(a.n_obj, (int)(blockIdx.x + 1) * per_block);
     const bool vec4 = (a.k_wgt & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.weights_indices) |
                                               reinterpret_cast<uintptr_t>(a.weights)) & 15) == 0;
-    for (int g = blockIdx.x * per_block + threadIdx.x; g < g_end; g += blockDim.x) {
-        float* x = a.means3D + ((size_t)e * a.P + g) * 3;
-        const float px = x[0], py = x[1], pz = x[2];
-        float ox = 0.f, oy = 0.f, oz = 0.f;
-        const int* wi = a.weights_indices + (size_t)g * a.k_wgt;
-        const float* ww = a.weights + (size_t)g * a.k_wgt;
-        auto bone = [&](int b, float wk) {
-            float tx, ty, tz;
-            if (use_R) {
-                const float4 r0 = T[3 * b], r1 = T[3 * b + 1], r2 = T[3 * b + 2];
-                tx = r0.x * px + r0.y * py + r0.z * pz + r0.w;
-                ty = r1.x * px + r1.y * py + r1.z * pz + r1.w;
-                tz = r2.x * px + r2.y * py + r2.z * pz + r2.w;
+    // `T` is either the shared-memory copy or the global table; the loop is instantiated once per address space
+    // (a pointer selected at run time would compile to generic loads, which cost several times an LDS here)
+    auto run = [&](const float4* __restrict__ T) {
+        for (int g = blockIdx.x * per_block + threadIdx.x; g < g_end; g += blockDim.x) {
+            float* x = a.means3D + ((size_t)e * a.P + g) * 3;
+            const float px = x[0], py = x[1], pz = x[2];
+            float ox = 0.f, oy = 0.f, oz = 0.f;
+            const int* wi = a.weights_indices + (size_t)g * a.k_wgt;
+            const float* ww = a.weights + (size_t)g * a.k_wgt;
+            auto bone = [&](int b, float wk) {
+                float tx, ty, tz;
+                if (use_R) {
+                    const float4 r0 = T[3 * b], r1 = T[3 * b + 1], r2 = T[3 * b + 2];
+                    tx = r0.x * px + r0.y * py + r0.z * pz + r0.w;
+                    ty = r1.x * px + r1.y * py + r1.z * pz + r1.w;
+                    tz = r2.x * px + r2.y * py + r2.z * pz + r2.w;
+                } else {
+                    const float4 o = b0[b], n = b1[b];
+                    tx = (px - o.x) + (n.x - o.x) + o.x;
+                    ty = (py - o.y) + (n.y - o.y) + o.y;
+                    tz = (pz - o.z) + (n.z - o.z) + o.z;
+                }
+                ox += tx * wk; oy += ty * wk; oz += tz * wk;
+            };
+            if (vec4) {   // rows of k_wgt entries start 16-byte aligned: four bones per 128-bit load
+                for (int k = 0; k < a.k_wgt; k += 4) {
+                    const int4 b = __ldg(reinterpret_cast<const int4*>(wi + k));
+                    const float4 w = __ldg(reinterpret_cast<const float4*>(ww + k));
+                    bone(b.x, w.x); bone(b.y, w.y); bone(b.z, w.z); bone(b.w, w.w);
+                }
             } else {
-                const float4 o = b0[b], n = b1[b];
-                tx = (px - o.x) + (n.x - o.x) + o.x;
-                ty = (py - o.y) + (n.y - o.y) + o.y;
-                tz = (pz - o.z) + (n.z - o.z) + o.z;
+                for (int k = 0; k < a.k_wgt; ++k) bone(__ldg(wi + k), __ldg(ww + k));
             }
-            ox += tx * wk; oy += ty * wk; oz += tz * wk;
-        };
-        if (vec4) {   // rows of k_wgt entries start 16-byte aligned: four bones per 128-bit load
-            for (int k = 0; k < a.k_wgt; k += 4) {
-                const int4 b = __ldg(reinterpret_cast<const int4*>(wi + k));
-                const float4 w = __ldg(reinterpret_cast<const float4*>(ww + k));
-                bone(b.x, w.x); bone(b.y, w.y); bone(b.z, w.z); bone(b.w, w.w);
-            }
-        } else {
-            for (int k = 0; k < a.k_wgt; ++k) bone(__ldg(wi + k), __ldg(ww + k));
+            x[0] = ox; x[1] = oy; x[2] = oz;
         }
-        x[0] = ox; x[1] = oy; x[2] = oz;
-    }
+    };
+    if (kStage && use_R) run(s_T);
+    else run(Rm);
 }
 
 }  // namespace

@@ -46,6 +46,8 @@ class EnvBatchConfig:
     seed: int = 1234
     env_offset: int = 0          # global index of this shard's first env (multi-GPU sharding)
     gripper: bool = True
+    pusher: bool = False         # the push-T tool instead of the gripper: one rigid rod (use_pusher, phystwin.py:462-510)
+    pusher_res: tuple = (112, 112)   # (n_circ, n_len) of the rod mesh: 112 x 112 = 25,312 triangles (the shipped STL has 25,368)
     success_start_frame: int | None = None   # None: the task's own (1700 / 800 / 350); frames before it do not count
     state_ring: int = 0          # frames of packed particle positions kept on the device (0 = none)
     instances_per_gaussian: float = 8.0
@@ -75,6 +77,8 @@ class BatchedEnv:
         poses = [synth.pose_scene(base, cfg.seed + cfg.env_offset + e) for e in range(E)]
         rest = np.stack([p.rest for p in poses])
         pr = dict(base.params)
+        if cfg.pusher:
+            pr["use_pusher"], pr["collide_eef_fric"] = True, 0.2     # phystwin.py:305-306
         self.phys = BatchedSpringMass(E, base.springs, rest, num_particles=base.N, n_substeps=cfg.n_substeps,
                                       log_spring_Y=base.log_Y, masses=base.mass, device=dev, **pr)
         self.x_init = torch.tensor(np.stack([p.x for p in poses]), device=dev)
@@ -94,7 +98,17 @@ class BatchedEnv:
             self.success = BatchedSuccess(task, E, base.N, obb=obb, **kw)
         # gripper: two fingers straddling the object near its centre, per-env motion tables
         self.gripper = None
-        if cfg.gripper:
+        if cfg.pusher:
+            # the rod stands just outside the object's -x face, tip 4 mm above the table; every env pushes along +x
+            tip = np.array([float(base.x[:, 0].min()) - 0.0375 + 0.0006, float(base.x[:, 1].mean()), 0.004])
+            self.gripper = g = synth.make_pusher(center=tip, n_circ=cfg.pusher_res[0], n_len=cfg.pusher_res[1])
+            self.phys.set_mesh(g.verts, g.faces, g.mesh_map, g.face_map, len(g.verts))
+            self.eef_init = tip.astype(np.float32)
+            table = np.repeat(g.verts[None], 2, 0)       # eef_pts_func(1.0) is all the pusher ever asks (phystwin.py:474-477)
+            self.eef = BatchedEefMotion(E, table, self.eef_init, dt=pr["dt"], n_substeps=cfg.n_substeps,
+                                        use_pusher=True, phys=self.phys, device=dev)
+            self.eef_pose = np.zeros((E, 3), np.float32)
+        elif cfg.gripper:
             ctr = base.x.mean(0)
             self.gripper = synth.make_gripper(center=(float(ctr[0]), float(ctr[1]), 0.004), gap=0.03)
             g = self.gripper
@@ -197,6 +211,13 @@ class BatchedEnv:
         gripper_openness (E,) -- 19 floats per environment instead of the (S,48,3) vertex tables."""
         cfg, E = self.cfg, self.cfg.E
         rng = np.random.default_rng(cfg.seed + 1000 * frame + cfg.env_offset)
+        if cfg.pusher:   # push along +x with a little sideways drift and yaw; the opening is not used (None)
+            vel = np.stack([rng.uniform(0.05, 0.3, E), rng.uniform(-0.03, 0.03, E), np.zeros(E)], 1).astype(np.float32)
+            rot_vel = np.stack([np.zeros(E), np.zeros(E), rng.normal(0.0, 0.5, E)], 1).astype(np.float32)
+            xyz = (self.eef_init[None] + self.eef_pose).astype(np.float32)
+            rot = np.repeat(synth.EEF_ROT_DOWN[None], E, 0).astype(np.float32)
+            self.eef_pose = self.eef_pose + vel * np.float32(self.dt * cfg.n_substeps)
+            return xyz, vel, rot, rot_vel, None
         vel = rng.uniform(-0.1, 0.1, (E, 3)).astype(np.float32)
         vel[:, 2] = rng.uniform(-0.05, 0.02, E)
         rot_vel = rng.normal(0.0, 0.2, (E, 3)).astype(np.float32)

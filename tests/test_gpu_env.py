@@ -100,3 +100,44 @@ def test_command_driven_env_closed_loop_matches_the_oracles():
         off = np.abs(x - o.x).max(1) > 1e-5
         assert off.mean() <= 0.01, f"frame {f}: {off.sum()} particles beyond 1e-5 m"   # contact ties, see DESIGN.md §2
     assert torch.isfinite(env.color).all()
+
+
+def test_pusher_env_driven_by_commands_matches_the_oracles():
+    """The push-T tool in the batched env: a rigid rod (use_pusher) whose per-substep vertex table comes from the
+    device-side end-effector step (opening fixed at 1.0, one velocity row); the CPU side runs oracle/eef_ref.py
+    + oracle/physics_ref.c with the same commands."""
+    import torch
+    import r2s_testutil as util
+    from oracle import eef_ref
+    from real2sim_eval_b200 import synth
+    from real2sim_eval_b200.envs import BatchedEnv, EnvBatchConfig
+    cfg = EnvBatchConfig(scene="tblock", E=2, W=64, H=64, n_substeps=20, P=3000, gripper=False, pusher=True,
+                         pusher_res=(24, 16))
+    env = BatchedEnv(cfg, "cuda")
+    assert env.phys.use_pusher and len(env.gripper.faces) == 816
+    e = 1
+    x0 = env.phys.get_state()[0][e].cpu().numpy()
+    sc = synth.pose_scene(env.base, cfg.seed + e)
+    o = util.oracle_from_scene(sc, cfg.n_substeps, mesh=util.gripper_mesh_dict(env.gripper), use_pusher=True,
+                               collide_eef_fric=0.2)
+    assert np.array_equal(o.x, x0)
+    if env.phys.self_collision:
+        o.create_resting_case()
+    o_free = util.oracle_from_scene(sc, cfg.n_substeps)
+    table = env.eef.table.cpu().numpy()
+    for f in range(2):
+        cmd = env.make_commands(f)
+        env.step(command=tuple(None if a is None else torch.tensor(a).cuda().contiguous() for a in cmd))
+        xyz, vel, rot, rvel = (a[e] for a in cmd[:4])
+        r = eef_ref.eef_step(table, env.eef_init, xyz, vel, rot, rvel, 1.0, dt=env.dt, n_substeps=cfg.n_substeps,
+                             use_pusher=True)
+        o.set_mesh_interactive(r["interp_pts"], r["interp_center"], r["dyn_vel"], r["dyn_omega"])
+        if env.phys.self_collision:
+            o.update_collision_graph(); o_free.update_collision_graph()
+        o.step(); o_free.step()
+        x = env.phys.get_state()[0][e].cpu().numpy()
+        off = np.abs(x - o.x).max(1) > 1e-5
+        assert off.mean() <= 0.01, f"frame {f}: {off.sum()} particles beyond 1e-5 m"
+    assert np.abs(o.x - o_free.x).max() > 1e-4, "the rod must push the block"
+    assert float(env.eef.current_openness[e]) == 1.0
+    assert torch.isfinite(env.color).all()

@@ -130,3 +130,29 @@ def test_metrics_allgather_world_size_2_gloo(tmp_path):
     assert all(p.returncode == 0 for p in procs), outs
     res = json.loads(outs[0][0].strip().splitlines()[-1])
     assert res["got"] == [[0.0, 5.0, 10.0], [1.0, 5.0, 35.0]] and res["max"] == 11.0
+
+
+def test_eef_and_metrics_host_helpers_need_no_gpu():
+    """Host-side pieces of the N3 / N4 rows: the force rows the grasp test reads, the routing box, argument
+    checks that fire before any device work."""
+    import numpy as np
+    import pytest
+    from oracle import eef_ref, metrics_ref
+    from real2sim_eval_b200 import _lib, eef, metrics, synth
+    g = synth.make_gripper((0.5, 0.0, 0.03))
+    assert eef.force_faces(g.mesh_map) == eef_ref.force_faces(g.mesh_map) == [18, 19, 1, 44 + 18, 44 + 19, 44 + 1]
+    with pytest.raises(ValueError, match="faces 18, 19 and 1"):
+        eef.force_faces(np.zeros(10, np.int32))
+    lo, hi = metrics.rope_box()
+    rlo, rhi = metrics_ref.rope_box()
+    assert np.array_equal(lo, rlo) and np.array_equal(hi, rhi)
+    assert metrics.START_FRAME == metrics_ref.START_FRAME and metrics.NEED_FRAMES == metrics_ref.NEED_FRAMES == 30
+    with pytest.raises(_lib.R2SError, match="no CPU path"):
+        eef.BatchedEefMotion(1, synth.gripper_opening_table((0, 0, 0)), (0, 0, 0), dt=5e-5, n_substeps=4,
+                             mesh_map=g.mesh_map, device="cpu")
+    with pytest.raises(ValueError, match="unknown task"):
+        metrics.BatchedSuccess("fold", 1, 4)
+    t = synth.gripper_opening_table((0.5, 0.0, 0.03))
+    assert t.shape == (101, 48, 3) and t.dtype == np.float32
+    gap = lambda k: t[k, 24:, 1].mean() - t[k, :24, 1].mean()
+    assert abs(gap(0) - 0.008) < 1e-6 and abs(gap(100) - 0.08) < 1e-6 and gap(50) > gap(49)

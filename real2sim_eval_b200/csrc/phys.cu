@@ -89,6 +89,7 @@ struct FrameParams {
     const float* frec;          // [F][24] rest-frame face record: v0 v1 v2 | n | e01 e12 e20 | pad
     const float* vnorm;         // [V][3] angle-weighted vertex pseudonormals
     const int* cell_start;      // [ncell + 1]
+    const unsigned char* cell_skip;  // [ncell] Chebyshev distance in cells to the nearest non-empty cell
     const int* cell_tris;       // triangle ids per cell
     float gx0, gy0, gz0, gh;    // grid origin, cell edge
     int gnx, gny, gnz;
@@ -187,12 +188,15 @@ __device__ __forceinline__ int closest_bary_region(float3 a, float3 b, float3 c,
 struct GridView {  // the fields of FrameParams the grid query needs, passed by value (kernel parameters live in
                    // the constant bank; taking a reference to the whole struct would copy it to local memory)
     const float* frec; const float* vnorm; const int* cell_start; const int* cell_tris; const int* faces;
+    const unsigned char* cell_skip;
     float gx0, gy0, gz0, gh;
     int gnx, gny, gnz, sign_mode;
 };
 
-__device__ __noinline__ bool mesh_query_grid(const GridView p, float3 q, float max_dist, int& face, float3& c_rest,
-                                             float& sign)
+constexpr int kTriQueue = 256;   // triangle ids a warp collects before testing them 32 at a time
+
+__device__ __noinline__ bool mesh_query_grid(const GridView p, float3 q, float max_dist, int* queue, int& face,
+                                             float3& c_rest, float& sign)
 {
     const unsigned kFull = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -203,27 +207,63 @@ __device__ __noinline__ bool mesh_query_grid(const GridView p, float3 q, float m
     float best = max_dist * max_dist;
     int hit = 0x7fffffff, region = 0;
     float bu = 0.f, bv = 0.f;
+    auto test = [&](int fc) {
+        const float* fr = p.frec + (size_t)fc * 24;
+        const float3 a = f3(fr[0], fr[1], fr[2]), b = f3(fr[3], fr[4], fr[5]), c = f3(fr[6], fr[7], fr[8]);
+        float uu, vv;
+        const int reg = closest_bary_region(a, b, c, q, uu, vv);
+        const float3 cp = a * uu + b * vv + c * (1.0f - uu - vv);
+        const float3 d = cp - q;
+        const float d2 = dot3(d, d);
+        if (d2 < best || (d2 == best && fc < hit)) { best = d2; hit = fc; bu = uu; bv = vv; region = reg; }
+    };
+    // Lanes enumerate the cells of a shell, but most cells are empty: the triangle ids of the non-empty ones are
+    // first compacted into the warp's queue and then tested one per lane, so the (expensive) closest-point test
+    // runs on full warps.  The result does not depend on the order (minimum distance, ties to the lower face).
+    int qn = 0;   // warp-uniform fill of the queue
+    auto drain = [&]() {
+        __syncwarp();
+        for (int j = lane; j < qn; j += 32) test(queue[j]);
+        __syncwarp();
+        qn = 0;
+    };
     const int r_max = (int)ceilf(max_dist * inv_h) + 1;
-    for (int r = 0; r <= r_max; ++r) {
+    // shells closer than the nearest non-empty cell hold no triangle: start there (nothing in reach: no hit)
+    const int r_first = p.cell_skip[(cz * p.gny + cy) * p.gnx + cx];
+    for (int r = r_first; r <= r_max; ++r) {
         const int w = 2 * r + 1, n_cells = w * w * w;
-        for (int k = lane; k < n_cells; k += 32) {
-            const int dz = k / (w * w) - r, dy = (k / w) % w - r, dx = k % w - r;
-            if (max(max(abs(dx), abs(dy)), abs(dz)) != r) continue;  // interior cells were visited by earlier shells
-            const int x = cx + dx, y = cy + dy, z = cz + dz;
-            if (x < 0 || y < 0 || z < 0 || x >= p.gnx || y >= p.gny || z >= p.gnz) continue;
-            const int cell = (z * p.gny + y) * p.gnx + x;
-            for (int t = p.cell_start[cell]; t < p.cell_start[cell + 1]; ++t) {
-                const int fc = p.cell_tris[t];
-                const float* fr = p.frec + (size_t)fc * 24;
-                const float3 a = f3(fr[0], fr[1], fr[2]), b = f3(fr[3], fr[4], fr[5]), c = f3(fr[6], fr[7], fr[8]);
-                float uu, vv;
-                const int reg = closest_bary_region(a, b, c, q, uu, vv);
-                const float3 cp = a * uu + b * vv + c * (1.0f - uu - vv);
-                const float3 d = cp - q;
-                const float d2 = dot3(d, d);
-                if (d2 < best || (d2 == best && fc < hit)) { best = d2; hit = fc; bu = uu; bv = vv; region = reg; }
+        for (int k0 = 0; k0 < n_cells; k0 += 32) {
+            const int k = k0 + lane;
+            int t0 = 0, cnt = 0;
+            if (k < n_cells) {
+                const int dz = k / (w * w) - r, dy = (k / w) % w - r, dx = k % w - r;
+                const int x = cx + dx, y = cy + dy, z = cz + dz;
+                // interior cells were visited by earlier shells
+                if (max(max(abs(dx), abs(dy)), abs(dz)) == r && x >= 0 && y >= 0 && z >= 0 && x < p.gnx && y < p.gny &&
+                    z < p.gnz) {
+                    const int cell = (z * p.gny + y) * p.gnx + x;
+                    t0 = p.cell_start[cell];
+                    cnt = p.cell_start[cell + 1] - t0;
+                }
             }
+            if (!__any_sync(kFull, cnt > 0)) continue;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(kFull, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int total = __shfl_sync(kFull, incl, 31);
+            if (total > kTriQueue) {   // a batch of very crowded cells: test them cell by cell
+                for (int t = t0; t < t0 + cnt; ++t) test(p.cell_tris[t]);
+                continue;
+            }
+            if (qn + total > kTriQueue) drain();
+            int* dst = queue + qn + incl - cnt;
+            for (int i = 0; i < cnt; ++i) dst[i] = p.cell_tris[t0 + i];
+            qn += total;
         }
+        drain();
         float wb = best;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) wb = fminf(wb, __shfl_xor_sync(kFull, wb, o));
@@ -353,6 +393,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
     if (p.stage_dyn) sp += sizeof(float) * 3 * ((p.n_dyn + 3) & ~3);
     float* s_forces = reinterpret_cast<float*>(sp);
     if (p.smem_forces) sp += sizeof(float) * 3 * p.F;
+    int* s_triq = reinterpret_cast<int*>(sp);                                // [warps][kTriQueue] (grid accelerator only)
 
     const bool has_mesh = p.F > 0;
     const float dt = p.dt, rf = p.rf;
@@ -671,9 +712,9 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                     const float3 qr = f3(R[0] * w.x + R[3] * w.y + R[6] * w.z, R[1] * w.x + R[4] * w.y + R[7] * w.z,
                                          R[2] * w.x + R[5] * w.y + R[8] * w.z);
                     float3 cr;
-                    const GridView gv = {p.frec, p.vnorm, p.cell_start, p.cell_tris, p.faces, p.gx0, p.gy0, p.gz0, p.gh,
+                    const GridView gv = {p.frec, p.vnorm, p.cell_start, p.cell_tris, p.faces, p.cell_skip, p.gx0, p.gy0, p.gz0, p.gh,
                                          p.gnx, p.gny, p.gnz, p.sign_mode};
-                    if (!mesh_query_grid(gv, qr, 0.02f, qface, cr, qsign)) return false;
+                    if (!mesh_query_grid(gv, qr, 0.02f, s_triq + (tid >> 5) * kTriQueue, qface, cr, qsign)) return false;
                     qpc = f3(R[0] * cr.x + R[1] * cr.y + R[2] * cr.z + R[9], R[3] * cr.x + R[4] * cr.y + R[5] * cr.z + R[10],
                              R[6] * cr.x + R[7] * cr.y + R[8] * cr.z + R[11]);
                     return true;
@@ -1092,6 +1133,7 @@ struct r2s_phys {
     float* frec = nullptr;
     float* vnorm = nullptr;
     int* cell_start = nullptr;
+    unsigned char* cell_skip = nullptr;
     int* cell_tris = nullptr;
     float grid0[3] = {0, 0, 0}, grid_h = 0.f;
     int grid_n[3] = {0, 0, 0};
@@ -1128,6 +1170,7 @@ int configure_launch(r2s_phys* h)
         misc += sizeof(int) * ((N + 3) & ~3);  // queue of particles near the mesh
         if (dynb <= 24 * 1024 && !h->accel) { h->stage_dyn = 1; misc += dynb; }
         if (fb <= 24 * 1024) { h->smem_forces = 1; misc += fb; }
+        if (h->accel) misc += sizeof(int) * 32 * 256;   // per-warp triangle queues of mesh_query_grid (kTriQueue)
     }
     size_t state = sizeof(float4) * 2 * (size_t)N + sizeof(float) * 3 * ((N + 3) & ~3);
     h->smem_state = state + misc + 256 <= (size_t)h->max_smem_optin;
@@ -1270,6 +1313,33 @@ int build_accel(r2s_phys* h, const float* verts, const int* faces, int V, int F)
             R2S_CUDA_TRY(cudaMemcpy(h->cell_start, start.data(), sizeof(int) * start.size(), cudaMemcpyHostToDevice));
             if (!tris.empty())
                 R2S_CUDA_TRY(cudaMemcpy(h->cell_tris, tris.data(), sizeof(int) * tris.size(), cudaMemcpyHostToDevice));
+            // Chebyshev distance (in cells, capped) from every cell to the nearest non-empty one: two 3-D chamfer
+            // sweeps, exact for the chessboard metric.  A query starts its shell search at that radius.
+            const int nx = h->grid_n[0], ny = h->grid_n[1], nz = h->grid_n[2];
+            std::vector<unsigned char> skip((size_t)ncell);
+            for (long long i = 0; i < ncell; ++i) skip[i] = start[i + 1] > start[i] ? 0 : 255;
+            auto at = [&](int x, int y, int z) -> int {
+                return (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz) ? 255 : skip[((size_t)z * ny + y) * nx + x];
+            };
+            for (int sweep = 0; sweep < 2; ++sweep) {
+                const int dir = sweep ? -1 : 1;
+                for (int zz = 0; zz < nz; ++zz)
+                    for (int yy = 0; yy < ny; ++yy)
+                        for (int xx = 0; xx < nx; ++xx) {
+                            const int x = sweep ? nx - 1 - xx : xx, y = sweep ? ny - 1 - yy : yy, z = sweep ? nz - 1 - zz : zz;
+                            int best_d = at(x, y, z);
+                            for (int dz = -1; dz <= 1; ++dz)      // the 13 neighbours already swept in this direction
+                                for (int dy = -1; dy <= 1; ++dy)
+                                    for (int dx = -1; dx <= 1; ++dx) {
+                                        const int lin = (dz * 3 + dy) * 3 + dx;
+                                        if (lin * dir >= 0) continue;
+                                        best_d = std::min(best_d, at(x + dx, y + dy, z + dz) + 1);
+                                    }
+                            skip[((size_t)z * ny + y) * nx + x] = (unsigned char)std::min(best_d, 255);
+                        }
+            }
+            if (dmalloc(&h->cell_skip, skip.size())) return R2S_ERR_CUDA;
+            R2S_CUDA_TRY(cudaMemcpy(h->cell_skip, skip.data(), skip.size(), cudaMemcpyHostToDevice));
         }
     }
     h->accel = 1;
@@ -1395,7 +1465,7 @@ int r2s_phys_destroy(r2s_phys* h)
     void* ptrs[] = {h->row_ptr, h->nbr, h->sid, h->nbr_k, h->rest_csr, h->logY, h->mass, h->mask, h->x4, h->v4,
                     h->vb_scratch, h->coll_num, h->coll_idx, h->status, h->resting, h->key_scratch,
                     h->stat_verts, h->faces, h->mesh_map, h->face_map, h->dyn_part, h->coll_forces, h->interp_pts,
-                    h->interp_center, h->dyn_vel, h->dyn_omega, h->frec, h->vnorm, h->cell_start, h->cell_tris};
+                    h->interp_center, h->dyn_vel, h->dyn_omega, h->frec, h->vnorm, h->cell_start, h->cell_tris, h->cell_skip};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     delete h;
@@ -1483,9 +1553,9 @@ int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, con
     for (void* p : old)
         if (p) cudaFree(p);
     h->interp_pts = h->interp_center = h->dyn_vel = h->dyn_omega = nullptr;
-    for (void* q : {(void*)h->frec, (void*)h->vnorm, (void*)h->cell_start, (void*)h->cell_tris})
+    for (void* q : {(void*)h->frec, (void*)h->vnorm, (void*)h->cell_start, (void*)h->cell_tris, (void*)h->cell_skip})
         if (q) cudaFree(q);
-    h->frec = h->vnorm = nullptr; h->cell_start = h->cell_tris = nullptr; h->accel = 0;
+    h->frec = h->vnorm = nullptr; h->cell_start = h->cell_tris = nullptr; h->cell_skip = nullptr; h->accel = 0;
     h->V = V; h->F = F; h->n_dyn = n_dyn;
     const int E = h->d.E, ns = h->d.n_substeps;
     if (dmalloc(&h->stat_verts, (size_t)3 * V) || dmalloc(&h->faces, (size_t)3 * F) || dmalloc(&h->mesh_map, F) ||
@@ -1651,7 +1721,7 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     p.omega_stride = pe * 3;
     p.coll_forces = h->coll_forces;
     p.accel = h->accel;
-    p.frec = h->frec; p.vnorm = h->vnorm; p.cell_start = h->cell_start; p.cell_tris = h->cell_tris;
+    p.frec = h->frec; p.vnorm = h->vnorm; p.cell_start = h->cell_start; p.cell_tris = h->cell_tris; p.cell_skip = h->cell_skip;
     p.gx0 = h->grid0[0]; p.gy0 = h->grid0[1]; p.gz0 = h->grid0[2]; p.gh = h->grid_h;
     p.gnx = h->grid_n[0]; p.gny = h->grid_n[1]; p.gnz = h->grid_n[2];
     p.a0 = h->anchors[0]; p.a1 = h->anchors[1]; p.a2 = h->anchors[2];

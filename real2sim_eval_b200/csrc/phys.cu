@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
+#include <map>
 #include <vector>
 
 #include "r2s_internal.h"
@@ -75,6 +76,8 @@ struct FrameParams {
     const int* mesh_map;      // [F]
     const int* face_map;      // [F]
     const int* dyn_part;      // [n_dyn] part (0..kMaxParts-1) of each dynamic vertex: one bounding box per part
+    int grp[15];              // face groups {first, end, closed} x (kMaxParts + 1); n_grp = 0 disables grouping
+    int n_grp;
     const float* interp_pts;  // [(E)][n_sub_table][n_dyn][3]
     long long interp_stride;  // per env (0 = shared)
     const float* interp_center;  // [(E)][n_sub_table][3]
@@ -99,11 +102,19 @@ struct FrameParams {
 };
 
 // ------------------------------------------------------------------ mesh query
+constexpr int kMaxParts = 4;                               // separately boxed parts of the dynamic mesh
+constexpr float kBoxGrow = 0.005f * 1.0001f + 1e-6f;       // the largest contact margin (+ slack)
+
 struct MeshView {
     const float* dyn;   // staged (shared) or table row (global): n_dyn x 3
     const float* stat;  // global rest-pose vertices
     const int* faces;
     int n_dyn, F;
+    // face groups (one per dynamic part + one for the static faces): [k] = {first face, end face, closed?}, and
+    // their bounding boxes of this substep (6 floats each, lo then hi); n_grp = 0: no grouping, scan every face
+    const int* grp;
+    const float* boxes;
+    int n_grp;
     __device__ __forceinline__ float3 vert(int idx) const
     {
         const float* p = idx < n_dyn ? dyn + 3 * idx : stat + 3 * idx;
@@ -318,15 +329,50 @@ __device__ __noinline__ bool mesh_query_warp(const MeshView& m, float3 p, float 
     float best = max_dist * max_dist;
     int hit = 0x7fffffff;
     float bu = 0.f, bv = 0.f;
-    for (int fc = lane; fc < m.F; fc += 32) {
-        const int* t = m.faces + 3 * fc;
-        float3 a = m.vert(t[0]), b = m.vert(t[1]), c = m.vert(t[2]);
-        float uu, vv;
-        closest_bary(a, b, c, p, uu, vv);
-        float3 q = a * uu + b * vv + c * (1.0f - uu - vv);
-        float3 d = q - p;
-        float d2 = dot3(d, d);
-        if (d2 < best) { best = d2; hit = fc; bu = uu; bv = vv; }
+    auto scan = [&](int f0, int f1) {
+        for (int fc = f0 + lane; fc < f1; fc += 32) {
+            const int* t = m.faces + 3 * fc;
+            float3 a = m.vert(t[0]), b = m.vert(t[1]), c = m.vert(t[2]);
+            float uu, vv;
+            closest_bary(a, b, c, p, uu, vv);
+            float3 q = a * uu + b * vv + c * (1.0f - uu - vv);
+            float3 d = q - p;
+            float d2 = dot3(d, d);
+            if (d2 < best || (d2 == best && fc < hit)) { best = d2; hit = fc; bu = uu; bv = vv; }
+        }
+    };
+    // squared distance from p to each group's box (0 inside): no face of the group is closer than that, so groups
+    // are scanned nearest box first and the scan stops at the first box farther than the best hit so far --
+    // the same arg-min (ties to the lower face) as the scan over all faces
+    float gd[kMaxParts + 1];
+#pragma unroll
+    for (int k = 0; k <= kMaxParts; ++k) {
+        gd[k] = 3e38f;
+        if (k < m.n_grp && m.grp[3 * k + 1] > m.grp[3 * k]) {
+            const float* b = m.boxes + 6 * k;
+            const float ex = fmaxf(fmaxf(b[0] - p.x, p.x - b[3]), 0.0f), ey = fmaxf(fmaxf(b[1] - p.y, p.y - b[4]), 0.0f),
+                        ez = fmaxf(fmaxf(b[2] - p.z, p.z - b[5]), 0.0f);
+            gd[k] = ex * ex + ey * ey + ez * ez;
+        }
+    }
+    if (m.n_grp == 0) {
+        scan(0, m.F);
+    } else {
+        unsigned seen = 0u;
+        for (int it = 0; it < m.n_grp; ++it) {
+            int kmin = -1;
+            float dmin = 3e38f;
+#pragma unroll
+            for (int k = 0; k <= kMaxParts; ++k)
+                if (!((seen >> k) & 1u) && gd[k] < dmin) { dmin = gd[k]; kmin = k; }
+            if (kmin < 0) break;
+            seen |= 1u << kmin;
+            float wb = best;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) wb = fminf(wb, __shfl_xor_sync(kFull, wb, o));
+            if (dmin > wb) break;   // every remaining group is at least this far
+            scan(m.grp[3 * kmin], m.grp[3 * kmin + 1]);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -341,9 +387,21 @@ __device__ __noinline__ bool mesh_query_warp(const MeshView& m, float3 p, float 
     face = hit; u = bu; v = bv;
     if (sign_mode == 1) { sign = 1.0f; return true; }
     float total = 0.0f;
-    for (int fc = lane; fc < m.F; fc += 32) {
-        const int* t = m.faces + 3 * fc;
-        total += solid_angle(m.vert(t[0]), m.vert(t[1]), m.vert(t[2]), p);
+    auto wind = [&](int f0, int f1) {
+        for (int fc = f0 + lane; fc < f1; fc += 32) {
+            const int* t = m.faces + 3 * fc;
+            total += solid_angle(m.vert(t[0]), m.vert(t[1]), m.vert(t[2]), p);
+        }
+    };
+    if (m.n_grp == 0) {
+        wind(0, m.F);
+    } else {
+        // a CLOSED group (every edge shared by two opposite half-edges) subtends a total solid angle of exactly 0
+        // from any point outside it, in particular from outside its box: only open groups and groups whose box
+        // contains p are summed (the omitted terms are rounding noise ~1e-7 against the 0.6 threshold)
+#pragma unroll
+        for (int k = 0; k <= kMaxParts; ++k)
+            if (k < m.n_grp && !(m.grp[3 * k + 2] && gd[k] > 0.0f)) wind(m.grp[3 * k], m.grp[3 * k + 1]);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(kFull, total, o);
@@ -363,9 +421,6 @@ __device__ __forceinline__ float3 mesh_eval(const MeshView& m, int face, float u
 // kPrecise: IEEE sqrt / divisions in the reference's expression order (SMW:87-99).
 // !kPrecise: one rsqrt + Newton step gives 1/len, the rest length is stored as its reciprocal;
 // same formula, ~4x fewer instructions per spring, results within a few ulp of the precise path.
-constexpr int kMaxParts = 4;                               // separately boxed parts of the dynamic mesh
-constexpr float kBoxGrow = 0.005f * 1.0001f + 1e-6f;       // the largest contact margin (+ slack)
-
 template <int G, bool kSmemState, bool kPrecise, bool kAccel>
 __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
 {
@@ -394,6 +449,8 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
     float* s_forces = reinterpret_cast<float*>(sp);
     if (p.smem_forces) sp += sizeof(float) * 3 * p.F;
     int* s_triq = reinterpret_cast<int*>(sp);                                // [warps][kTriQueue] (grid accelerator only)
+    __shared__ int s_grp[3 * (kMaxParts + 1)];
+    if (tid < 3 * (kMaxParts + 1)) s_grp[tid] = p.grp[tid];
 
     const bool has_mesh = p.F > 0;
     const float dt = p.dt, rf = p.rf;
@@ -616,6 +673,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
         if (has_mesh) {
             mesh.dyn = p.stage_dyn ? s_dyn : g_interp + (size_t)step * p.n_dyn * 3;
             mesh.stat = p.stat_verts; mesh.faces = p.faces; mesh.n_dyn = p.n_dyn; mesh.F = p.F;
+            mesh.grp = s_grp; mesh.boxes = s_aabb; mesh.n_grp = p.n_grp;
             // merged box of dynamic + static vertices, grown by the largest contact margin (+ slack).
             // A query can only change a particle that is inside the mesh (then it is inside the box) or
             // closer than `margin` (5 mm fingers, 1 mm otherwise) to its surface: a hit between margin and
@@ -1121,6 +1179,8 @@ struct r2s_phys {
     int* mesh_map = nullptr;
     int* face_map = nullptr;
     int* dyn_part = nullptr;
+    int grp[15] = {0};
+    int n_grp = 0;
     float* coll_forces = nullptr;
     float* interp_pts = nullptr;
     float* interp_center = nullptr;
@@ -1581,6 +1641,41 @@ int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, con
         h->dyn_part = nullptr;
         if (dmalloc(&h->dyn_part, part.size())) return R2S_ERR_CUDA;
         R2S_CUDA_TRY(cudaMemcpy(h->dyn_part, part.data(), sizeof(int) * part.size(), cudaMemcpyHostToDevice));
+        // face groups for the brute-force query: group = part of the face's (dynamic) vertices, 4 = static faces.
+        // Usable only if every face lies in one group and each group is one contiguous face range; a group is
+        // closed when every directed edge a->b has exactly one partner b->a inside the group.
+        bool ok = true;
+        std::vector<int> fg(F, 0);
+        for (int f = 0; f < F && ok; ++f) {
+            const int* t = faces + 3 * f;
+            const bool d0 = t[0] < n_dyn, d1 = t[1] < n_dyn, d2 = t[2] < n_dyn;
+            if (d0 && d1 && d2) {
+                fg[f] = part[t[0]];
+                ok = part[t[1]] == fg[f] && part[t[2]] == fg[f];
+            } else if (!d0 && !d1 && !d2) {
+                fg[f] = 4;
+            } else {
+                ok = false;
+            }
+        }
+        for (int k = 0; k < 15; ++k) h->grp[k] = 0;
+        for (int g = 0; g < 5 && ok; ++g) {
+            int first = -1, last = -1, count = 0;
+            for (int f = 0; f < F; ++f)
+                if (fg[f] == g) { if (first < 0) first = f; last = f; ++count; }
+            if (count == 0) continue;
+            ok = last - first + 1 == count;
+            std::map<std::pair<int, int>, int> half;   // directed edge -> multiplicity
+            for (int f = first; f <= last && ok; ++f)
+                for (int c = 0; c < 3; ++c) half[{faces[3 * f + c], faces[3 * f + (c + 1) % 3]}]++;
+            bool closed = true;
+            for (const auto& kv : half) {
+                const auto it = half.find({kv.first.second, kv.first.first});
+                if (kv.second != 1 || it == half.end() || it->second != 1) { closed = false; break; }
+            }
+            h->grp[3 * g] = first; h->grp[3 * g + 1] = last + 1; h->grp[3 * g + 2] = closed ? 1 : 0;
+        }
+        h->n_grp = ok ? 5 : 0;
     }
     // SMW:699-711 defaults: rest pose repeated over the substeps, centre = mean, zero velocities
     std::vector<float> tbl((size_t)ns * n_dyn * 3 + 1), ctr((size_t)ns * 3 + 1), zero(6, 0.f);
@@ -1713,6 +1808,8 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     p.mass = h->mass; p.mask = h->mask; p.x4 = h->x4; p.v4 = h->v4; p.vb_scratch = h->vb_scratch;
     p.coll_num = h->coll_num; p.coll_idx = h->coll_idx; p.status = h->status;
     p.stat_verts = h->stat_verts; p.faces = h->faces; p.mesh_map = h->mesh_map; p.face_map = h->face_map; p.dyn_part = h->dyn_part;
+    for (int k = 0; k < 15; ++k) p.grp[k] = h->grp[k];
+    p.n_grp = h->n_grp;
     p.interp_pts = h->interp_pts; p.interp_center = h->interp_center; p.dyn_vel = h->dyn_vel; p.dyn_omega = h->dyn_omega;
     const long long pe = h->motion_per_env ? 1 : 0;
     p.interp_stride = pe * h->d.n_substeps * h->n_dyn * 3;

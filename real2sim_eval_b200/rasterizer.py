@@ -157,7 +157,10 @@ class BatchedRasterizer:
             super_count=view(L.tile_count, 4 * B * T, torch.int32).view(B, T),
             super_offset=view(L.tile_offset, 4 * (B * T + 1), torch.int32),
             keys=view(L.keys, 8 * cap, torch.int64),
-            sorted_rect=view(L.sorted_rect, 4 * cap, torch.int32),
+            sorted_rect=view(L.sorted_rect, 4 * cap, torch.int32),   # filled only when id_shift == 0
+            # low word of a key: id << id_shift | rectangle local to the super-tile (x0 | y0 << 3 | x1 << 6 | y1 << 9)
+            # when P <= 2^20 (id_shift = 12); else the id alone, with the rectangles in sorted_rect
+            id_shift=12 if P <= (1 << 20) else 0,
             tiles=(L.tiles_x, L.tiles_y),
             supers=(L.super_x, L.super_y),
         )

@@ -79,13 +79,20 @@ def _tile_lists(r, view=0):
     off, keys, rects, it = _super_lists(r, view)
     gx, gy = it["tiles"]
     sgx = it["supers"][0]
+    sh = it["id_shift"]
     out = []
     for ty in range(gy):
         for tx in range(gx):
             s = (ty // 4) * sgx + tx // 4
-            k, rc = keys[off[s]:off[s + 1]], rects[off[s]:off[s + 1]]
-            keep = (tx >= (rc & 255)) & (tx < ((rc >> 16) & 255)) & (ty >= ((rc >> 8) & 255)) & (ty < (rc >> 24))
-            out.append((k[keep] & np.uint64(0xffffffff)).astype(np.uint32))
+            k = keys[off[s]:off[s + 1]]
+            low = (k & np.uint64(0xffffffff)).astype(np.uint32)
+            if sh:   # rectangle local to the super-tile, packed under the id
+                lx, ly = tx % 4, ty % 4
+                keep = (lx >= (low & 7)) & (lx < ((low >> 6) & 7)) & (ly >= ((low >> 3) & 7)) & (ly < ((low >> 9) & 7))
+            else:
+                rc = rects[off[s]:off[s + 1]]
+                keep = (tx >= (rc & 255)) & (tx < ((rc >> 16) & 255)) & (ty >= ((rc >> 8) & 255)) & (ty < (rc >> 24))
+            out.append(low[keep] >> np.uint32(sh))
     return out
 
 
@@ -413,3 +420,26 @@ def test_rgb8_output_is_the_reference_host_conversion():
                   bg=torch.zeros(3).cuda(), W=cam.W, H=cam.H, tanfovx=cam.tanfovx, tanfovy=cam.tanfovy,
                   shs=t["shs"], scales=t["scales"], rotations=t["rotations"], views_per_scene=B,
                   out_rgb8=torch.empty((B, cam.H, cam.W, 3), dtype=torch.float32, device="cuda"))
+
+
+def test_more_than_2_pow_20_gaussians_use_the_gathered_rectangle_path():
+    """Keys carry id << 12 | local rectangle only while ids fit 20 bits; beyond that the id fills the low word
+    and the rectangles are gathered after the sort.  1,053,576 Gaussians (most behind the camera): the lists
+    and images must still be the oracle's."""
+    P_vis, P_far = 5000, (1 << 20)
+    g = _util.small_gaussians(31, P_vis, scale=0.02)
+    far = _util.small_gaussians(32, P_far, box=((5.0, -0.5, 0.0), (8.0, 0.5, 0.5)), scale=0.01)   # behind the eye
+    order = np.random.default_rng(5).permutation(P_vis + P_far)
+    g = {k: np.concatenate([g[k], far[k]])[order] for k in g}
+    cam = _util.make_test_camera(64, 64)
+    r, color, radii, depth, total, overflow = _run_cuda(g, cam, max_instances=400000)
+    assert not overflow and r.intermediates()["id_shift"] == 0
+    oc, orad, od, aux = _run_oracle(g, cam, aux=True)
+    assert (orad > 0).sum() > 1000 and (orad == 0).sum() > P_far // 2
+    assert np.array_equal(radii, orad)
+    if np.array_equal(r.intermediates()["depths"][0].cpu().numpy(), aux["depths"]):
+        for t, ids in enumerate(_tile_lists(r)):
+            r0, r1 = aux["ranges"][t]
+            assert np.array_equal(ids, aux["point_list"][r0:r1]), f"tile {t}"
+    _close_images(color, oc, "P > 2^20")
+    _close_images(depth, od, "P > 2^20 depth")

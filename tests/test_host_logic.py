@@ -156,3 +156,17 @@ def test_eef_and_metrics_host_helpers_need_no_gpu():
     assert t.shape == (101, 48, 3) and t.dtype == np.float32
     gap = lambda k: t[k, 24:, 1].mean() - t[k, :24, 1].mean()
     assert abs(gap(0) - 0.008) < 1e-6 and abs(gap(100) - 0.08) < 1e-6 and gap(50) > gap(49)
+
+
+def test_launch_summary_tool_reads_the_committed_launch_list():
+    """tools/launch_summary.py on profiles/r01b_launches_256envs.csv: the compositing kernel dominates a step."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    csv_path = os.path.join(root, "profiles", "r01b_launches_256envs.csv")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "launch_summary.py"), csv_path, "--steps", "3"],
+                         capture_output=True, text=True, check=True).stdout
+    rows = [l for l in out.splitlines() if "share of one step" in l and "%" in l]
+    assert rows[0].startswith("composite_kernel") and len(rows) >= 10
+    shares = [float(l.split("share of one step")[1].replace("%", "")) for l in rows]
+    assert abs(sum(shares) - 100.0) < 0.5 and shares[0] > 50.0

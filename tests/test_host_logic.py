@@ -170,3 +170,30 @@ def test_launch_summary_tool_reads_the_committed_launch_list():
     assert rows[0].startswith("composite_kernel") and len(rows) >= 10
     shares = [float(l.split("share of one step")[1].replace("%", "")) for l in rows]
     assert abs(sum(shares) - 100.0) < 0.5 and shares[0] > 50.0
+
+
+def test_super_tile_local_rectangle_is_equivalent_to_the_global_one():
+    """The invariant behind the packed sort keys (raster.cu emit_kernel / composite_kernel): for every tile
+    rectangle [minx, maxx) x [miny, maxy) and every 4x4 super-tile it touches, a tile of that super-tile lies in
+    the rectangle iff its local coordinates lie in the rectangle clipped to the super-tile and made local --
+    computed as the kernel does (only the first / last super-tile of a row or column is cut)."""
+    K = 4
+    n = 0
+    for minx in range(0, 13):
+        for maxx in range(minx + 1, 14):
+            sx0, sx1 = minx // K, (maxx + K - 1) // K
+            for sx in range(sx0, sx1):
+                x0 = minx - K * sx0 if sx == sx0 else 0
+                x1 = maxx - K * sx if sx == sx1 - 1 else K
+                assert 0 <= x0 <= 3 and 1 <= x1 <= 4, (minx, maxx, sx)
+                # the same values as the straightforward clip
+                assert x0 == min(max(minx - K * sx, 0), K) and x1 == min(max(maxx - K * sx, 0), K)
+                for lx in range(K):
+                    tx = K * sx + lx
+                    assert (minx <= tx < maxx) == (x0 <= lx < x1)
+                    n += 1
+    assert n > 1000
+    # packing: four 3-bit fields under the id
+    low = (123456 << 12) | (1 | (2 << 3) | (4 << 6) | (3 << 9))
+    assert (low & 7, (low >> 3) & 7, (low >> 6) & 7, (low >> 9) & 7, low >> 12) == (1, 2, 4, 3, 123456)
+    assert ((1 << 20) - 1) << 12 < (1 << 32), "ids below 2^20 fit above the 12 rectangle bits"

@@ -497,10 +497,15 @@ static void mesh_collision(oracle_phys *s, int step)
                 v3 v_tao_new = muls(v_tao, a);
                 next_v = add(v_normal_new, v_tao_new);
                 if (is_gripper >= 1) next_v = add(next_v, real_dyn);
+                /* SMW:397 re-assigns `query`: for a finger / tool contact the force is booked on the face of the
+                 * re-query (SMW:414); a missed re-query leaves Warp's default-constructed result (face 0) */
+                int force_face = face;
                 if (is_gripper >= 1) {
                     next_x = add(x0, muls(next_v, dt));
                     int face2; float u2, v2, sign2;
+                    force_face = 0;
                     if (mesh_query(s, next_x, 0.02f, 0.6f, &face2, &u2, &v2, &sign2)) {
+                        force_face = face2;
                         v3 p2 = mesh_eval(s, face2, u2, v2);
                         v3 delta2 = sub(next_x, p2);
                         float dist2 = len(delta2) * sign2;
@@ -514,7 +519,7 @@ static void mesh_collision(oracle_phys *s, int step)
                     next_x = sub(next_x, muls(normal, err));
                 }
                 v3 delta_v_normal = sub(v_normal_new, v_normal);
-                int fm = s->face_map[face]; /* first query's face (SMW:414) */
+                int fm = s->face_map[force_face];
                 st(s->collision_forces, fm, add(ld(s->collision_forces, fm), divs(delta_v_normal, dt)));
             }
         }

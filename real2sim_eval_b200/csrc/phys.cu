@@ -810,10 +810,15 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         const float3 v_tao_new = v_tao * a;
                         next_v = v_normal_new + v_tao_new;
                         if (is_gripper >= 1) next_v = next_v + real_dyn;
+                        // SMW:397 re-assigns `query`, so the force of a finger / tool contact is booked on the face
+                        // of the RE-QUERY (SMW:414); a missed re-query leaves Warp's default-constructed result, face 0
+                        int force_face = face;
                         if (is_gripper >= 1) {
                             next_x = x0 + next_v * dt;
                             int face2; float sign2; float3 p2;
+                            force_face = 0;
                             if (query(next_x, face2, p2, sign2)) {
+                                force_face = face2;
                                 const float3 delta2 = next_x - p2;
                                 const float err2 = len3(delta2) * sign2 - margin;
                                 if (err2 < 0.0f) {
@@ -826,7 +831,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         }
                         if (lane == 0 && step == p.n_sub - 1) {
                             const float3 dvn = (v_normal_new - v_normal) / dt;
-                            const int fm = p.face_map[face];
+                            const int fm = p.face_map[force_face];
                             atomicAdd(forces + 3 * fm, dvn.x);
                             atomicAdd(forces + 3 * fm + 1, dvn.y);
                             atomicAdd(forces + 3 * fm + 2, dvn.z);

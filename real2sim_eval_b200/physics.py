@@ -315,7 +315,8 @@ class SpringMassSystemWarp:
             collide_eef_fric=g(collide_eef_fric, "collide_eef_fric"),
             collide_self_elas=g(collide_self_elas, "collide_self_elas"),
             collide_self_fric=g(collide_self_fric, "collide_self_fric"),
-            use_pusher=use_pusher, sign_mode=sign_mode, precise=precise, device=self.device)
+            use_pusher=use_pusher, sign_mode=sign_mode, precise=precise, coll_row_cap=500,   # SMW:544-549
+            device=self.device)
         self.wp_state = _State(self.sys)
         v0 = None if init_velocities is None else init_velocities[:num_object_points]
         self.set_init_state(init_vertices, v0)
@@ -343,8 +344,9 @@ class SpringMassSystemWarp:
             self.num_eefs = n_dyn_meshes // 2 if not self.use_pusher else n_dyn_meshes
             assert self.num_eefs <= 1
             self.num_dynamic_points = len(dynamic_points)
+            self._face_map = np.concatenate(face_map, 0)
             self.sys.set_mesh(np.concatenate(vertices, 0), np.concatenate(indices, 0), np.concatenate(mesh_map, 0),
-                              np.concatenate(face_map, 0), self.num_dynamic_points)
+                              self._face_map, self.num_dynamic_points)
             self.all_meshes_warp = self.sys  # truthiness only: "a mesh exists"
             self.num_dynamic_velocities = self.num_eefs * 2 if not self.use_pusher else self.num_eefs
         if self.self_collision:
@@ -360,6 +362,23 @@ class SpringMassSystemWarp:
     @property
     def collision_forces(self):
         return DeviceArray(self.sys.collision_forces[0])
+
+    @property
+    def face_map(self):
+        return DeviceArray(torch.as_tensor(self._face_map))
+
+    @property
+    def wp_collision_number(self):          # SMW:550-552
+        return DeviceArray(self.sys.coll_num[0])
+
+    @property
+    def wp_collision_indices(self):         # SMW:544-549, (N, 500)
+        return DeviceArray(self.sys.coll_idx[0])
+
+    @property
+    def collision_row_overflow(self) -> int:
+        """Candidates dropped because a row was full (the reference would write out of bounds); blocking read."""
+        return int(self.sys.status[0, 1])
 
     def create_resting_case(self):
         self.sys.create_resting_case()

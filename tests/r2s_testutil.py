@@ -60,3 +60,43 @@ def make_test_camera(W, H, eye=(0.9, 0.05, 0.5), target=(0.0, 0.0, 0.15), fov_de
     fx = 0.5 * W / np.tan(np.radians(fov_deg) / 2)
     k = np.array([[fx, 0, W / 2.0 - 0.3], [0, fx, H / 2.0 + 0.2], [0, 0, 1]])
     return synth.setup_camera(W, H, k, np.linalg.inv(c2w))
+
+
+# ---------------------------------------------------------------------------- physics cases (tests/phys_cases.py)
+def load_phys_golden(name):
+    """tests/golden/phys_<name>.npz (outputs of the reference's own spring_mass_warp.py, see
+    tests/golden/make_physics_golden.py) + the case rebuilt from the seeded builders; the input digest must agree."""
+    import os
+    import phys_cases
+    case = phys_cases.CASES[name]()
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"phys_{name}.npz"))
+    assert str(g["input_sha"]) == phys_cases.input_digest(case), f"{name}: seeded inputs drifted from the golden's"
+    return case, g
+
+
+def oracle_from_case(case, **kw):
+    import phys_cases
+    o = oracle_from_scene(case["scene"], case["n_substeps"], mesh=phys_cases.merged_mesh(case),
+                          use_pusher=case["use_pusher"], **case["over"], **kw)
+    if case["reset"] is not None:
+        o.x[:], o.v[:] = case["reset"]
+    return o
+
+
+def cuda_from_case(case, E=1, **kw):
+    import phys_cases
+    c = cuda_from_scenes([case["scene"]] * E, case["n_substeps"], per_env_rest=False, use_pusher=case["use_pusher"],
+                         **case["over"], **kw)
+    m = phys_cases.merged_mesh(case)
+    if m is not None:
+        c.set_mesh(**m)
+    if case["reset"] is not None:
+        x, v = case["reset"]
+        c.set_state(np.repeat(x[None], E, 0), np.repeat(v[None], E, 0))
+    return c
+
+
+def golden_coll_rows(g, k):
+    """Candidate rows of frame k as a list of arrays."""
+    num = g[f"f{k}_coll_num"]
+    return num, np.split(g[f"f{k}_coll_flat"], np.cumsum(num)[:-1]) if len(num) else []

@@ -64,6 +64,7 @@ def parse():
     ap.add_argument("--cpu-sample-envs", type=int, default=0, help="cpu_baseline sample size (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fast", action="store_true", help="skip the fast-composite variant measured beside the headline")
     return ap.parse_args()
 
 
@@ -123,6 +124,47 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local: int):
+    """Pin this process to the cores of its GPU's NUMA node BEFORE any pinned host memory is allocated, so the
+    D2H targets live on the node the GPU's PCIe root port hangs off.  Returns a description for the JSON line.
+    (On a single-node host -- the 8-GPU box of round 1 reports NUMA 0 / CPUs 0-31 for every GPU -- this is a no-op.)"""
+    info = {"numa_node": None, "cpus": None, "bound": False}
+    try:
+        prop = torch.cuda.get_device_properties(local)
+        bdf = f"{prop.pci_domain_id:04x}:{prop.pci_bus_id:02x}:{prop.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["pci"] = bdf
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
+        if node < 0 or len(nodes) <= 1:
+            info["numa_node"] = node
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info.update(numa_node=node, cpus=len(allowed), bound=True)
+    except Exception as ex:   # no sysfs / no permission: report and carry on unbound
+        info["error"] = str(ex)[:80]
+    return info
+
+
+def config_label(args):
+    """Which BASELINE.json config the arguments describe (configs[1] is the headline the metric is quoted on)."""
+    W, H = args.res
+    key = (args.scene, args.envs, W, H, args.cameras, args.substeps)
+    if key == ("rope", 256, 512, 512, 1, 10):
+        return "BASELINE configs[1]"
+    if key == ("sloth", 64, 640, 480, 2, 10):
+        return "BASELINE configs[2]"
+    if args.scene == "tblock" and (W, H) == (256, 256):
+        return "BASELINE configs[3] shape with rendering"
+    return "custom shape"
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -139,6 +181,7 @@ def run_ours(args):
     rank, world, local = dist_env()
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    binding = bind_to_gpu_numa_node(local)      # before the first pinned allocation
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -212,7 +255,7 @@ def run_ours(args):
         env.links.forward(m[5], env.means3D, env.rotations)
         pe3[k].record()
         env.raster.forward(env.means3D, env.opacities, viewmatrix=env.view, projmatrix=env.proj, campos=env.campos,
-                           bg=env.bg, W=W, H=H, tanfovx=env.cams[0].tanfovx, tanfovy=env.cams[0].tanfovy, shs=env.shs,
+                           bg=env.bg, W=W, H=H, tanfovx=env.tanfovx, tanfovy=env.tanfovy, shs=env.shs,
                            scales=env.scales, rotations=env.rotations, sh_degree=0, z_threshold=0.05,
                            views_per_scene=cfg.cameras, max_instances=env.max_instances, out_color=env.color,
                            out_depth=env.depth, want_radii=False)
@@ -229,9 +272,39 @@ def run_ours(args):
     eef_ms = float(np.mean([a.elapsed_time(b) for a, b in zip(pem, pe0)]))   # incl. the x_prev copy
     lib.r2s_raster_set_profile(0)
     total, overflow = env.raster.status()
+    if overflow:
+        raise RuntimeError(f"instance capacity exceeded in the timed region ({total} > {env.max_instances})")
+    env.check()                                 # sticky overflow counter + candidate-row overflow, outside the timed region
     from real2sim_eval_b200 import shard
     ms_max = shard.max_over_ranks(ms_total, dev)
     value = world * E * args.steps / (ms_max / 1e3)
+
+    # ---- the same loop with the fast compositing variant (ex2.approx; 1e-4 relative contract, not bit-identical):
+    # reported beside the headline, never as the headline
+    fast_variant = None
+    if not args.no_fast:
+        env.cfg.fast_composite = True
+        for i in range(args.warmup):
+            env.step(command=motions_dev[i][:5], link_pose=motions_dev[i][5])
+        lib.r2s_raster_set_profile(1)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for k in range(args.steps):
+            m = motions_dev[args.warmup + k]
+            env.step(command=m[:5], link_pose=m[5])
+        f1.record()
+        barrier()
+        _lib.check(lib.r2s_raster_get_profile(prof), "get_profile")
+        lib.r2s_raster_set_profile(0)
+        fms = shard.max_over_ranks(f0.elapsed_time(f1), dev)
+        fast_variant = {"value": world * E * args.steps / (fms / 1e3), "unit": UNIT, "ms_per_step": fms / args.steps,
+                        "composite_ms": round(float(prof[4]), 4),
+                        "what": "composite_mode=FAST: log2(e) folded into the staged conic + ex2.approx instead of the IEEE "
+                                "expf the bit-identical path keeps; held to 1e-4 relative vs the live reference in "
+                                "tests/test_gpu_raster.py::test_fast_composite_variant_within_contract"}
+        env.cfg.fast_composite = False
+        env.check()
 
     # ---- end-to-end loop: host buffers in, host buffers out, copies inside the timed region.
     # Device->host copies of step k (observations + particle state) run on a side stream while step k+1
@@ -240,7 +313,7 @@ def run_ours(args):
     # evaluation loop holds on the host, experiments/eval_policy.py:248) + float32 depth; "f32" = the
     # float32 CHW colour image + depth (the device-side tensors, 16 B/pixel).  The headline `e2e` is "u8";
     # the float variant is reported next to it.
-    e2e = e2e_f32 = None
+    e2e = None
     if not args.no_e2e:
         N = env.base.N
         import ctypes
@@ -249,11 +322,12 @@ def run_ours(args):
         phys_lib = env.phys.lib
         h2d = sum(t.numel() * 4 for t in acts_pinned[0]) + (env.view_h.numel() + env.proj_h.numel() + env.campos_h.numel()) * 4
 
-        def run_e2e(fmt, base_i):
+        def run_e2e(fmt, base_i, with_depth):
             hostbuf, devbuf = [], []
             for slot in range(2):
-                hb = dict(x=torch.empty((E, N, 3)).pin_memory(), v=torch.empty((E, N, 3)).pin_memory(),
-                          depth=torch.empty(env.depth.shape).pin_memory())
+                hb = dict(x=torch.empty((E, N, 3)).pin_memory(), v=torch.empty((E, N, 3)).pin_memory())
+                if with_depth:
+                    hb["depth"] = torch.empty(env.depth.shape).pin_memory()
                 color = env.color if slot == 0 else torch.empty_like(env.color)
                 depth = env.depth if slot == 0 else torch.empty_like(env.depth)
                 if fmt == "u8":
@@ -287,7 +361,8 @@ def run_ours(args):
                     hb = hostbuf[slot]
                     hb["x"].copy_(xs, non_blocking=True)
                     hb["v"].copy_(vs, non_blocking=True)
-                    hb["depth"].copy_(devbuf[slot][1], non_blocking=True)
+                    if with_depth:
+                        hb["depth"].copy_(devbuf[slot][1], non_blocking=True)
                     if fmt == "u8":
                         hb["rgb8"].copy_(devbuf[slot][2], non_blocking=True)
                     else:
@@ -310,9 +385,10 @@ def run_ours(args):
             last = hostbuf[(args.steps - 1) % 2]
             out = {"value": world * E * args.steps / (ms / 1e3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                    "d2h_bytes_per_step": int(d2h), "ms_per_step": ms / args.steps,
-                   "observations": ("rgb uint8 [B,H,W,3] (reference host format, eval_policy.py:248) + depth f32 "
-                                    "+ particle x,v f32" if fmt == "u8" else
-                                    "colour f32 [B,3,H,W] + depth f32 + particle x,v f32"),
+                   "observations": (("rgb uint8 [B,H,W,3] (reference host format, eval_policy.py:248)" if fmt == "u8" else
+                                     "colour f32 [B,3,H,W]") + (" + depth f32 [B,1,H,W]" if with_depth else "")
+                                    + " + particle x,v f32 [E,N,3]"),
+                   "host_buffers": {k: list(v.shape) for k, v in hostbuf[0].items()},
                    "overlap": "D2H of step k on a side stream under the compute of step k+1 (double-buffered outputs)"}
             if fmt == "u8":
                 out["checksum_rgb8_host"] = int(last["rgb8"].long().sum())
@@ -320,10 +396,15 @@ def run_ours(args):
                 out["checksum_rgb_host"] = float(last["color"].double().sum())
             return out
 
+        # headline: what the reference's evaluation loop moves to the host every step -- the RGB image
+        # (experiments/eval_policy.py:139-157, 248 copy RGB only; depth stays on the device) + the particle state it
+        # pickles (:209-213).  The variants that also bring the f32 depth / the f32 colour image are reported beside it.
         base_i = args.warmup + args.steps
-        e2e_f32 = run_e2e("f32", base_i)
-        e2e = run_e2e("u8", base_i + args.warmup + args.steps)
-        e2e["float_image_variant"] = e2e_f32
+        e2e = run_e2e("u8", base_i, with_depth=False)
+        e2e["with_depth_variant"] = run_e2e("u8", base_i, with_depth=True)
+        e2e["float_image_variant"] = run_e2e("f32", base_i + args.warmup + args.steps, with_depth=True)
+        e2e["host_binding"] = binding
+        env.check()
 
     clocks = sampler.stop()
     # ---- metrics all-gather (the only collective)
@@ -369,19 +450,31 @@ def run_ours(args):
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "ours",
         "config": {"workload": f"{cfg.scene} PhysTwin x {E} envs/GPU, {ns} substeps/step, {cfg.cameras} x {W}x{H} "
-                               f"render of {P} Gaussians per env (BASELINE configs[1])",
+                               f"render of {P} Gaussians per env ({config_label(args)})",
                    "envs_per_gpu": E, "global_envs": world * E, "particles": env.base.N, "springs": env.base.S,
                    "substeps": ns, "resolution": [W, H], "cameras": cfg.cameras, "gaussians_per_env": P,
                    "gaussian_rows": {"object_lbs": env.n_obj, "robot_links": env.n_robot, "static": P - env.n_obj - env.n_robot},
                    "instances_per_step": int(R), "instances_per_gaussian": round(R / (B * P), 3),
                    "super_tile_instances_per_step": int(env.raster.intermediates()["super_offset"][-1].item()),
                    "mean_tile_list": round(R / (B * T), 1), "parallelism": f"env-shard x{world}",
-                   "l2_policy": "inputs larger than L2 (2.9 GB of Gaussians + 1.07 GB of images per step)"},
+                   "l2_policy": "inputs larger than L2 (2.9 GB of Gaussians + 1.07 GB of images per step)",
+                   "outputs": "colour f32 CHW + depth f32 (+ uint8 HWC in e2e); the `radii` output of the reference API "
+                              "(205 MB per step, ~0.05 ms) is not requested in the loop (want_radii=False)"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
+        "fast_composite_variant": fast_variant,
         "metrics_allgather": {"per_rank": gathered, "fields": ["steps", "seconds", "checksum_x", "checksum_rgb", "episodes_succeeded", "frames_passed"]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # timed on rank 0 at N=1 only
-        line["cpu_baseline"] = cpu_baseline(args, env)
+        line["cpu_baseline"] = cb = cpu_baseline(args, env)
+        if cb.get("reference_rasterizer_us_per_view"):
+            ours_us = float(sum(stage_ms)) / env.B * 1e3
+            line["raster_vs_reference"] = {
+                "ours_us_per_view": round(ours_us, 2), "reference_us_per_view": round(cb["reference_rasterizer_us_per_view"], 2),
+                "ratio": round(cb["reference_rasterizer_us_per_view"] / ours_us, 2),
+                "what": f"five raster kernels of the last timed step / {env.B} views (CUDA events) vs the unmodified reference "
+                        "CUDA rasterizer (oracle/_ref) called view by view on the same device tensors with its blocking "
+                        "num_rendered read-back (wall clock, 3 passes over 16 envs); images bit-identical "
+                        "(tests/test_gpu_raster.py::test_bench_configurations_bit_identical_to_reference)"}
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
@@ -436,7 +529,33 @@ def cpu_baseline(args, env=None):
         list(ex.map(render, range(n)))
     t_rend = time.perf_counter() - t1
     dt = t_phys + t_rend
+    ref_raster_us = None
+    if env is not None:   # the UNMODIFIED reference CUDA rasterizer (oracle/_ref) on this run's own scenes, view by view
+        import ref_raster
+        if ref_raster.available():
+            dev = env.device
+            k = min(16, env.cfg.E)
+            color = torch.empty((3, H, W), device=dev)
+            depth = torch.empty((1, H, W), device=dev)
+            radii = torch.empty(env.cfg.P, dtype=torch.int32, device=dev)
+            views = [(e, c) for e in range(k) for c in range(env.cfg.cameras)]
+
+            def ref_pass():
+                for e, c in views:
+                    b = e * env.cfg.cameras + c
+                    t = dict(means3D=env.means3D[e], scales=env.scales[e], rotations=env.rotations[e],
+                             opacities=env.opacities[e], shs=env.shs[e])
+                    ref_raster.forward_torch(t, env.view[b], env.proj[b], env.campos[b], env.bg, W, H,
+                                             env.cams[b].tanfovx, env.cams[b].tanfovy, 0, 0.05, color, depth, radii)
+                torch.cuda.synchronize(dev)
+
+            ref_pass()
+            t2 = time.perf_counter()
+            for _ in range(3):
+                ref_pass()
+            ref_raster_us = (time.perf_counter() - t2) / (3 * len(views)) * 1e6
     return {"value": n / dt, "unit": UNIT, "cores": min(cores, n), "kind": "port",
+            "reference_rasterizer_us_per_view": ref_raster_us,
             "sample": f"{n} envs x 1 step ({args.substeps} substeps + one {W}x{H} render of {args.gaussians} Gaussians) "
                       f"with oracle/physics_ref.c + oracle/raster_ref.c, one env per host thread",
             "physics_s": round(t_phys, 4), "render_s": round(t_rend, 4),

@@ -68,7 +68,19 @@ typedef struct r2s_raster_args {
     size_t workspace_bytes;
     int64_t max_instances; /* capacity for (Gaussian, super-tile) instances over the whole batch; a
                               super-tile is 4x4 tiles, so the (Gaussian, tile) count is always enough */
+    const float* tanfov_views; /* [B,2] per-view (tanfovx, tanfovy) or NULL (every view uses tanfovx / tanfovy
+                                  above).  The reference builds one settings tuple per camera
+                                  (transform_utils.py:17-30); its fixed and wrist cameras differ in intrinsics */
+    int32_t* overflow_count;   /* device counter or NULL: incremented by every forward on which the instance lists
+                                  exceeded max_instances (that frame holds background only).  Sticky -- the caller
+                                  zeroes it and reads it when convenient, e.g. at the end of an episode */
+    int32_t composite_mode;    /* R2S_COMPOSITE_PRECISE (0): IEEE expf in the reference's expression order, images
+                                  bit-identical to the reference build.  R2S_COMPOSITE_FAST (1): log2(e) folded into
+                                  the staged conic and ex2.approx -- within the 1e-4 relative contract, not bitwise */
+    int32_t pad0_;
 } r2s_raster_args;
+#define R2S_COMPOSITE_PRECISE 0
+#define R2S_COMPOSITE_FAST 1
 
 size_t r2s_raster_workspace_bytes(int32_t B, int32_t P, int32_t W, int32_t H, int64_t max_instances);
 

@@ -13,6 +13,7 @@
 #include <cstdio>
 #include <functional>
 #include "rasterizer.h"
+#include "rasterizer_impl.h"
 
 namespace {
 struct Grow {
@@ -62,6 +63,25 @@ int ref_mark_visible(int P, float* means3D, float* viewmatrix, float* projmatrix
 {
     CudaRasterizer::Rasterizer::markVisible(P, means3D, viewmatrix, projmatrix, present);
     cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? 0 : -(int)e;
+}
+
+// The reference's own sorted instance list and per-tile ranges of the LAST forward call, located in its scratch
+// buffers with its own BinningState / ImageState::fromChunk (rasterizer_impl.cu:172-196), copied device to
+// device: point_list_out [num_rendered] Gaussian ids in (tile, depth) order, ranges_out [tiles][2].
+int ref_raster_lists(int num_rendered, int W, int H, unsigned* point_list_out, unsigned* ranges_out)
+{
+    if (!g_bin.ptr || !g_img.ptr) return -1;
+    char* bchunk = g_bin.ptr;
+    CudaRasterizer::BinningState bin = CudaRasterizer::BinningState::fromChunk(bchunk, (size_t)num_rendered);
+    char* ichunk = g_img.ptr;
+    CudaRasterizer::ImageState img = CudaRasterizer::ImageState::fromChunk(ichunk, (size_t)W * H);
+    const int tiles = ((W + 15) / 16) * ((H + 15) / 16);
+    cudaError_t e = cudaSuccess;
+    if (num_rendered > 0)
+        e = cudaMemcpy(point_list_out, bin.point_list, sizeof(unsigned) * (size_t)num_rendered, cudaMemcpyDeviceToDevice);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(ranges_out, img.ranges, sizeof(uint2) * (size_t)tiles, cudaMemcpyDeviceToDevice);
     return e == cudaSuccess ? 0 : -(int)e;
 }
 

@@ -66,14 +66,7 @@ class BatchedEefMotion:
         if phys is not None:
             if phys.n_substeps != self.S:
                 raise ValueError("the physics handle and the end-effector step disagree on n_substeps")
-            m = _lib.PhysMotion()
-            _lib.check(self.lib.r2s_phys_motion_ptrs(phys.h, 1, C.byref(m)), "r2s_phys_motion_ptrs")
-            if m.n_dyn_verts != self.V or m.n_env != self.E:
-                raise ValueError(f"physics mesh has {m.n_dyn_verts} dynamic vertices x {m.n_env} envs, "
-                                 f"table has {self.V} x {self.E}")
-            self._motion = (m.interp_pts, m.interp_center, m.dyn_vel, m.dyn_omega)
-            self.rows = int(m.dyn_vel_rows)
-            self._forces, self.F = phys.collision_forces, int(phys.collision_forces.shape[1])
+            self._bind()
         else:
             self.rows = 1 if use_pusher else 2
             self.interp_pts = torch.empty((self.E, self.S, self.V, 3), dtype=torch.float32, device=dev)
@@ -81,6 +74,26 @@ class BatchedEefMotion:
             self.dyn_vel = torch.zeros((self.E, self.rows, 3), dtype=torch.float32, device=dev)
             self.dyn_omega = torch.empty((self.E, 1, 3), dtype=torch.float32, device=dev)
             self._motion = tuple(t.data_ptr() for t in (self.interp_pts, self.interp_center, self.dyn_vel, self.dyn_omega))
+
+    def _bind(self):
+        """(Re-)query the bound physics handle's motion tables and force array.  The handle re-allocates them when
+        its mesh is replaced (r2s_phys_set_mesh) or when shared tables are installed (set_mesh_motion with
+        [S,V,3] tables flips the per-env mode), so cached pointers would dangle: forward() asks again every frame
+        (no re-allocation and no synchronisation happens while the mode stays per-env)."""
+        phys = self.phys
+        m = _lib.PhysMotion()
+        _lib.check(self.lib.r2s_phys_motion_ptrs(phys.h, 1, C.byref(m)), "r2s_phys_motion_ptrs")
+        if m.n_dyn_verts != self.V or m.n_env != self.E:
+            raise ValueError(f"physics mesh has {m.n_dyn_verts} dynamic vertices x {m.n_env} envs, "
+                             f"table has {self.V} x {self.E}")
+        self._motion = (m.interp_pts, m.interp_center, m.dyn_vel, m.dyn_omega)
+        self.rows = int(m.dyn_vel_rows)
+        p = _lib.PhysPtrs()
+        _lib.check(self.lib.r2s_phys_get_ptrs(phys.h, C.byref(p)), "r2s_phys_get_ptrs")
+        if self._forces is None or self._forces.data_ptr() != p.collision_forces:
+            phys._refresh_views()
+            self._forces = phys.collision_forces
+        self.F = int(self._forces.shape[1])
 
     def reset(self):
         """SpringMassDynamicsModule.__init__ state (phystwin.py:358-359)."""
@@ -91,6 +104,8 @@ class BatchedEefMotion:
         """eef_xyz/eef_vel/eef_rot_vel: [E,3]; eef_rot: [E,3,3]; gripper_openness: [E] (gripper only);
         collision_forces: [E,F,3] of the previous frame (default: the bound physics handle's, else zeros).
         Device float32 tensors.  Enqueues one kernel on the current stream."""
+        if self.phys is not None:
+            self._bind()
         f = collision_forces if collision_forces is not None else self._forces
         for name, t, n in (("eef_xyz", eef_xyz, 3), ("eef_vel", eef_vel, 3), ("eef_rot", eef_rot, 9),
                            ("eef_rot_vel", eef_rot_vel, 3), ("gripper_openness", gripper_openness, 1)):

@@ -51,6 +51,7 @@ class EnvBatchConfig:
     success_start_frame: int | None = None   # None: the task's own (1700 / 800 / 350); frames before it do not count
     state_ring: int = 0          # frames of packed particle positions kept on the device (0 = none)
     instances_per_gaussian: float = 8.0
+    fast_composite: bool = False  # ex2.approx compositing variant (1e-4 relative contract, not bit-identical)
 
 
 def _scene(name: str) -> synth.Scene:
@@ -179,6 +180,14 @@ class BatchedEnv:
         self.proj_h = torch.tensor(np.stack([c.proj for c in cams])).pin_memory()
         self.campos_h = torch.tensor(np.stack([c.campos for c in cams])).pin_memory()
         self.view, self.proj, self.campos = self.view_h.to(dev), self.proj_h.to(dev), self.campos_h.to(dev)
+        # one (tanfovx, tanfovy) per view when the cameras differ in intrinsics (the reference builds one settings
+        # tuple per camera, transform_utils.py:17-30)
+        tfx = np.array([c.tanfovx for c in cams], np.float32)
+        tfy = np.array([c.tanfovy for c in cams], np.float32)
+        if np.all(tfx == tfx[0]) and np.all(tfy == tfy[0]):
+            self.tanfovx, self.tanfovy = float(tfx[0]), float(tfy[0])
+        else:
+            self.tanfovx, self.tanfovy = torch.tensor(tfx, device=dev), torch.tensor(tfy, device=dev)
         self.bg = torch.zeros(3, device=dev)
         self.raster = BatchedRasterizer(dev)
         self.B = E * cfg.cameras
@@ -266,16 +275,34 @@ class BatchedEnv:
             self.phys.set_mesh_motion(*motion)
         self.x_prev4.copy_(self.phys.x4)             # state['x'] before the frame (gs_renderer.py:727)
         self.phys.step()
-        self.success.update(self.phys.x4)            # task test + episode counters (+ state ring) for this frame
+        # the reference pickles state/{cnt:06d}.pkl BEFORE env.step (eval_policy.py:209-225): file k is the state after
+        # k steps, so the state this frame produced is file number frame + 1
+        self.success.update(self.phys.x4, frame=self.frame + 1)
         self.lbs.forward(self.x_prev4, self.phys.x4, self.means3D)
         if self.links is not None and link_pose is not None:   # robot Gaussians follow this frame's FK poses
             self.links.forward(link_pose, self.means3D, self.rotations)
         c = self.cfg
         self.raster.forward(self.means3D, self.opacities, viewmatrix=self.view, projmatrix=self.proj,
-                            campos=self.campos, bg=self.bg, W=c.W, H=c.H, tanfovx=self.cams[0].tanfovx,
-                            tanfovy=self.cams[0].tanfovy, shs=self.shs, scales=self.scales, rotations=self.rotations,
+                            campos=self.campos, bg=self.bg, W=c.W, H=c.H, tanfovx=self.tanfovx,
+                            tanfovy=self.tanfovy, shs=self.shs, scales=self.scales, rotations=self.rotations,
                             sh_degree=0, z_threshold=0.05, views_per_scene=c.cameras,
                             max_instances=self.max_instances, out_color=color, out_depth=depth,
-                            want_radii=False, out_rgb8=rgb8)
+                            want_radii=False, out_rgb8=rgb8, fast=c.fast_composite)
         self.frame += 1
         return color, depth
+
+    def check(self):
+        """Raise if anything was silently dropped since the last call: a render whose instance lists overflowed the
+        workspace (that frame is background only), or self-collision candidates beyond the row capacity.  Both are
+        counted on the device without a per-frame synchronisation; this call synchronises -- use it at the end
+        of an episode (or of a benchmark's timed region)."""
+        lost = self.raster.overflows(reset=True)
+        if lost:
+            raise _lib.R2SError(f"{lost} frame(s) overflowed the rasterizer workspace (max_instances={self.max_instances}): "
+                                "raise EnvBatchConfig.instances_per_gaussian")
+        if self.phys.self_collision:
+            dropped = int(self.phys.status[:, 1].sum())
+            if dropped:
+                raise _lib.R2SError(f"{dropped} self-collision candidates exceeded the row capacity "
+                                    f"{self.phys.coll_row_cap} in the last frame (the reference keeps 500 per particle, "
+                                    "spring_mass_warp.py:544-549): construct the physics with a larger coll_row_cap")

@@ -66,6 +66,9 @@ class BatchedRasterizer:
         self.max_instances = 0
         self.shape = None
         self.layout = None
+        # sticky device counter: +1 for every forward whose instance lists overflowed the workspace (that frame
+        # holds background only); read with overflows() when convenient -- no per-frame synchronisation
+        self.overflow_count = torch.zeros(1, dtype=torch.int32, device=self.device)
 
     # ---- workspace
     def reserve(self, B, P, W, H, max_instances):
@@ -82,7 +85,11 @@ class BatchedRasterizer:
     def forward(self, means3D, opacities, *, viewmatrix, projmatrix, campos, bg, W, H, tanfovx, tanfovy,
                 shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, sh_degree=0,
                 scale_modifier=1.0, z_threshold=0.05, prefiltered=False, views_per_scene=1,
-                max_instances=None, out_color=None, out_depth=None, radii=None, want_radii=True, out_rgb8=None):
+                max_instances=None, out_color=None, out_depth=None, radii=None, want_radii=True, out_rgb8=None,
+                fast=False):
+        """tanfovx / tanfovy: floats shared by every view, or per-view sequences / tensors of length B (the
+        reference builds one settings tuple per camera, transform_utils.py:17-30).  fast=True selects the
+        ex2.approx compositing variant (within the 1e-4 relative contract, not bit-identical)."""
         dev = self.device
         means3D = _f32c(means3D, dev)
         viewmatrix = _f32c(viewmatrix, dev).reshape(-1, 16)
@@ -114,7 +121,17 @@ class BatchedRasterizer:
         a = _lib.RasterArgs()
         a.B, a.views_per_scene, a.P, a.D, a.M, a.W, a.H = B, views_per_scene, P, int(sh_degree), M, W, H
         a.prefiltered = int(bool(prefiltered))
-        a.scale_modifier, a.tanfovx, a.tanfovy, a.z_threshold = scale_modifier, tanfovx, tanfovy, z_threshold
+        tanfov_views = None
+        if not isinstance(tanfovx, (int, float)) or not isinstance(tanfovy, (int, float)):
+            tx = torch.as_tensor(tanfovx, dtype=torch.float32, device=dev).reshape(-1).expand(B) if not isinstance(tanfovx, (int, float)) \
+                else torch.full((B,), float(tanfovx), dtype=torch.float32, device=dev)
+            ty = torch.as_tensor(tanfovy, dtype=torch.float32, device=dev).reshape(-1).expand(B) if not isinstance(tanfovy, (int, float)) \
+                else torch.full((B,), float(tanfovy), dtype=torch.float32, device=dev)
+            tanfov_views = torch.stack([tx, ty], 1).contiguous()
+            tanfovx, tanfovy = 1.0, 1.0          # unused when the per-view table is given
+        a.scale_modifier, a.tanfovx, a.tanfovy, a.z_threshold = scale_modifier, float(tanfovx), float(tanfovy), z_threshold
+        a.tanfov_views, a.overflow_count = _ptr(tanfov_views), _ptr(self.overflow_count)
+        a.composite_mode = 1 if fast else 0
         a.means3D, a.scales, a.rotations, a.opacities = _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(opacities)
         a.shs, a.colors_precomp, a.cov3D_precomp = _ptr(shs), _ptr(colors_precomp), _ptr(cov3D_precomp)
         a.viewmatrix, a.projmatrix, a.campos, a.bg = _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), _ptr(bg)
@@ -127,7 +144,7 @@ class BatchedRasterizer:
         with torch.cuda.device(dev):
             _lib.check(self.lib.r2s_raster_forward(C.byref(a), _stream_ptr(dev)), "r2s_raster_forward")
         self._keep = (means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, viewmatrix,
-                      projmatrix, campos, bg)
+                      projmatrix, campos, bg, tanfov_views)
         return out_color, radii, out_depth
 
     def status(self):
@@ -136,6 +153,14 @@ class BatchedRasterizer:
         _lib.check(self.lib.r2s_raster_status(_ptr(self.ws), _stream_ptr(self.device), C.byref(n), C.byref(o)),
                    "r2s_raster_status")
         return int(n.value), bool(o.value)
+
+    def overflows(self, reset: bool = False) -> int:
+        """Number of forwards since the last reset whose instance lists overflowed max_instances (those frames
+        hold background only); synchronises the stream."""
+        n = int(self.overflow_count.item())
+        if reset:
+            self.overflow_count.zero_()
+        return n
 
     def intermediates(self):
         """Typed torch views of the workspace arrays (parity tests, accounting)."""

@@ -22,6 +22,9 @@ def lib():
         _lib.ref_raster_forward.argtypes = [i, i, i, vp, i, i, vp, vp, vp, vp, vp, f, vp, vp, vp, vp, vp, f, f, i, f,
                                             vp, vp, vp]
         _lib.ref_raster_forward.restype = i
+        if hasattr(_lib, "ref_raster_lists"):
+            _lib.ref_raster_lists.argtypes = [i, i, i, vp, vp]
+            _lib.ref_raster_lists.restype = i
     return _lib
 
 
@@ -54,3 +57,17 @@ def forward(g, cam, sh_degree=0, bg=(0.0, 0.0, 0.0)):
                       sh_degree, cam.z_threshold, color, depth, radii)
     torch.cuda.synchronize()
     return color.cpu().numpy(), radii.cpu().numpy(), depth.cpu().numpy(), n
+
+
+def lists(num_rendered, W, H):
+    """The reference's own sorted point_list [num_rendered] and tile ranges [tiles, 2] of the last forward()
+    (read out of its binning / image buffers with its own fromChunk layout)."""
+    import torch
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    pl = torch.zeros(max(num_rendered, 1), dtype=torch.int32, device="cuda")
+    rg = torch.zeros((tiles, 2), dtype=torch.int32, device="cuda")
+    rc = lib().ref_raster_lists(int(num_rendered), W, H, C.c_void_p(pl.data_ptr()), C.c_void_p(rg.data_ptr()))
+    if rc != 0:
+        raise RuntimeError(f"ref_raster_lists failed: {rc}")
+    torch.cuda.synchronize()
+    return pl[:num_rendered].cpu().numpy().view(np.uint32), rg.cpu().numpy().view(np.uint32)

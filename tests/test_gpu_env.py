@@ -32,6 +32,8 @@ def test_sloth_two_cameras_640x480():
     assert tuple(color.shape) == (6, 3, 480, 640) and tuple(depth.shape) == (6, 1, 480, 640)
     assert torch.isfinite(color).all() and float(color.min()) >= 0.0 and float(depth.max()) <= 15.0
     assert not torch.equal(color[0], color[1]), "the two cameras of one env see different images"
+    assert env.cams[0].tanfovx != env.cams[1].tanfovx, "and differ in intrinsics: one (tanfovx, tanfovy) per view"
+    env.check()
     x1 = env.phys.get_state()[0]
     assert torch.isfinite(x1).all() and float((x1 - x0).abs().max()) > 1e-6 and float(x1[..., 2].min()) > -1e-6
     # object Gaussians follow the particles (LBS): they stay within a few mm of their bound particles
@@ -42,8 +44,8 @@ def test_sloth_two_cameras_640x480():
     from real2sim_eval_b200.rasterizer import BatchedRasterizer
     r = BatchedRasterizer("cuda")
     c1, _, d1 = r.forward(env.means3D[1:2], env.opacities[1:2], viewmatrix=env.view[3:4], projmatrix=env.proj[3:4],
-                          campos=env.campos[3:4], bg=env.bg, W=640, H=480, tanfovx=env.cams[0].tanfovx,
-                          tanfovy=env.cams[0].tanfovy, shs=env.shs[1:2], scales=env.scales[1:2],
+                          campos=env.campos[3:4], bg=env.bg, W=640, H=480, tanfovx=env.cams[3].tanfovx,
+                          tanfovy=env.cams[3].tanfovy, shs=env.shs[1:2], scales=env.scales[1:2],
                           rotations=env.rotations[1:2], max_instances=2_000_000)
     assert torch.equal(c1[0], color[3]) and torch.equal(d1[0], depth[3])
 

@@ -37,6 +37,33 @@ def _check_state(x, v, g, k, name):
     return float(dx.max())
 
 
+def _plane_groups(case):
+    """Faces of the merged mesh grouped by (mesh part, supporting plane).  A contact whose closest point lies on the
+    edge shared by two coplanar triangles (the diagonal of a quad) is an exact tie between them: the reference
+    resolves it by BVH traversal order, a brute-force scan by face index, and 1-ulp differences in the distance
+    decide it either way -- so per-face forces are compared after summing over coplanar neighbours."""
+    m = phys_cases.merged_mesh(case)
+    v, f = m["verts"].astype(np.float64), m["faces"]
+    n = np.cross(v[f[:, 1]] - v[f[:, 0]], v[f[:, 2]] - v[f[:, 0]])
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    d = (n * v[f[:, 0]]).sum(1)
+    key = np.concatenate([m["mesh_map"][:, None], np.round(n * 1e4), np.round(d * 1e6)[:, None]], 1)
+    _, grp = np.unique(key, axis=0, return_inverse=True)
+    return grp.reshape(-1)
+
+
+def _check_forces(got, want, case):
+    grp = _plane_groups(case)
+    ng = grp.max() + 1
+    sg, sw = np.zeros((ng, 3)), np.zeros((ng, 3))
+    np.add.at(sg, grp, got)
+    np.add.at(sw, grp, want)
+    scale = np.abs(want).max()
+    assert np.abs(sg - sw).max() <= 2e-3 * scale + 1e-3, "per-plane contact forces differ from the reference's"
+    same_face = np.abs(got - want).max(1) <= 2e-3 * scale + 1e-3
+    assert same_face.mean() >= 0.9, "more than a few faces lost their force to a coplanar neighbour"
+
+
 def _check_candidates(num, idx, g, k):
     want_num, rows = util.golden_coll_rows(g, k)
     assert np.array_equal(num, want_num), f"frame {k}: candidate counts differ from the reference's"
@@ -67,8 +94,8 @@ def test_batched_kernels_match_the_reference_source(name, precise):
         if case["meshes"] is not None:
             want = g[f"f{k}_collision_forces"]
             got = c.collision_forces[0].cpu().numpy()
-            if HOLD[name][2] == 0.0:                        # no particle may have changed branch: forces agree per face
-                assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max() + 1e-3
+            if HOLD[name][2] == 0.0:                        # no particle may have changed branch: forces agree per plane
+                _check_forces(got, want, case)
             else:                                           # a few contacts flipped: the total impulse still agrees
                 assert np.abs(got.sum(0) - want.sum(0)).max() <= 0.05 * np.abs(want).sum(0).max() + 1.0
 
@@ -96,24 +123,25 @@ def test_dropin_class_driven_like_the_reference(name):
         v = wp.to_torch(sim.wp_state.wp_v).cpu().numpy()
         _check_state(x, v, g, k, name)
         if case["meshes"] is not None and HOLD[name][2] == 0.0:
-            want = g[f"f{k}_collision_forces"]
-            assert np.abs(sim.collision_forces.numpy() - want).max() <= 2e-3 * np.abs(want).max() + 1e-3
+            _check_forces(sim.collision_forces.numpy(), g[f"f{k}_collision_forces"], case)
 
 
 def test_grasp_force_faces_follow_the_requery():
     """SMW:397 re-assigns `query`, so a finger contact books its force on the face of the re-query (SMW:414);
     phystwin.py:386-391 reads faces [18], [19], [1] of each finger from that array.  The golden's per-face
-    forces come from the reference source, so per-face agreement pins the attribution."""
+    forces come from the reference source: agreement per supporting plane in every frame (exact ties between
+    coplanar triangles aside, see _plane_groups) and per face in the tie-free first frame pins the attribution."""
     case, g = util.load_phys_golden("gripper_graze")
     c = util.cuda_from_case(case, precise=True)
     for k, tables in enumerate(case["frames"]):
         c.update_collision_graph(); c.set_mesh_motion(*tables); c.step()
         want = g[f"f{k}_collision_forces"]
         got = c.collision_forces[0].cpu().numpy()
-        touched = np.abs(want).max(1) > 0
-        assert touched.sum() >= 4
-        assert np.array_equal(np.abs(got).max(1) > 0, touched), "forces landed on different faces"
-        assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max()
+        assert (np.abs(want).max(1) > 0).sum() >= 4
+        _check_forces(got, want, case)
+        if k == 0:   # no exact tie in this frame: every face carries the reference's force (first-query booking
+            #          moves the force of faces 4/5 and 60/61 to their coplanar neighbour and fails here)
+            assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max()
 
 
 def test_dense_contact_exceeds_the_compact_row_capacity():

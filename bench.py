@@ -279,6 +279,34 @@ def run_ours(args):
     ms_max = shard.max_over_ranks(ms_total, dev)
     value = world * E * args.steps / (ms_max / 1e3)
 
+    # ---- the same loop, pipelined: everything up to the sort on a high-priority stream, the compositing kernel on a
+    # second stream (r2s_raster_args.composite_stream), so the latency / memory-bound front end of step k+1 runs under
+    # the issue-bound compositing of step k.  Same kernels, same results; reported beside the headline because the
+    # per-kernel times of the roofline are those of the serial loop above.
+    hi, lo = torch.cuda.Stream(dev, priority=-1), torch.cuda.Stream(dev, priority=0)
+    main_stream = torch.cuda.current_stream(dev)
+
+    def pipelined(n, first):
+        hi.wait_stream(main_stream); lo.wait_stream(main_stream)
+        with torch.cuda.stream(hi):
+            for k in range(n):
+                m = motions_dev[first + k]
+                env.step(command=m[:5], link_pose=m[5], composite_stream=lo)
+        main_stream.wait_stream(hi); main_stream.wait_stream(lo)
+
+    pipelined(args.warmup, 0)
+    barrier()
+    q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    q0.record()
+    pipelined(args.steps, args.warmup)
+    q1.record()
+    barrier()
+    pms = shard.max_over_ranks(q0.elapsed_time(q1), dev)
+    pipelined_variant = {"value": world * E * args.steps / (pms / 1e3), "unit": UNIT, "ms_per_step": pms / args.steps,
+                         "what": "two streams: physics .. sort of step k+1 (high priority) under the compositing kernel of "
+                                 "step k (composite_stream); identical kernels and images"}
+    env.check()
+
     # ---- the same loop with the fast compositing variant (ex2.approx; 1e-4 relative contract, not bit-identical):
     # reported beside the headline, never as the headline
     fast_variant = None
@@ -317,7 +345,7 @@ def run_ours(args):
     if not args.no_e2e:
         N = env.base.N
         import ctypes
-        main = torch.cuda.current_stream(dev)
+        main = hi                                    # the step runs on the high-priority stream, its compositing on `lo`
         cs = torch.cuda.Stream(dev)
         phys_lib = env.phys.lib
         h2d = sum(t.numel() * 4 for t in acts_pinned[0]) + (env.view_h.numel() + env.proj_h.numel() + env.campos_h.numel()) * 4
@@ -345,17 +373,19 @@ def run_ours(args):
                 ev.record(cs)
 
             def e2e_step(i, slot):
+              with torch.cuda.stream(main):
                 m = upload(i)                                    # H2D: end-effector commands + link poses (pinned -> device)
                 env.view.copy_(env.view_h, non_blocking=True)    # H2D: cameras
                 env.proj.copy_(env.proj_h, non_blocking=True)
                 env.campos.copy_(env.campos_h, non_blocking=True)
                 main.wait_event(copied[slot])                    # the buffers of step i-2 have left the device
-                env.step(command=m[:5], out=devbuf[slot], link_pose=m[5])
+                env.step(command=m[:5], out=devbuf[slot], link_pose=m[5], composite_stream=lo)
                 xs, vs = devstate[slot]
                 _lib.check(phys_lib.r2s_phys_get_state(env.phys.h, ctypes.c_void_p(xs.data_ptr()),
                                                        ctypes.c_void_p(vs.data_ptr()),
                                                        ctypes.c_void_p(main.cuda_stream)), "get_state")
-                computed[slot].record(main)
+                lo.wait_stream(main)                             # images (lo) and state (main) of this step are complete
+                computed[slot].record(lo)
                 with torch.cuda.stream(cs):                      # D2H on the side stream
                     cs.wait_event(computed[slot])
                     hb = hostbuf[slot]
@@ -374,9 +404,11 @@ def run_ours(args):
             cs.synchronize()
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            main.wait_stream(main_stream); lo.wait_stream(main_stream)
             e0.record(main)
             for i in range(args.steps):
                 e2e_step(base_i + args.warmup + i, i % 2)
+            main.wait_stream(lo)
             main.wait_stream(cs)                                 # all copies have landed
             e1.record(main)
             cs.synchronize()
@@ -389,7 +421,8 @@ def run_ours(args):
                                      "colour f32 [B,3,H,W]") + (" + depth f32 [B,1,H,W]" if with_depth else "")
                                     + " + particle x,v f32 [E,N,3]"),
                    "host_buffers": {k: list(v.shape) for k, v in hostbuf[0].items()},
-                   "overlap": "D2H of step k on a side stream under the compute of step k+1 (double-buffered outputs)"}
+                   "overlap": "D2H of step k on a side stream under the compute of step k+1 (double-buffered outputs); "
+                              "the compositing kernel on its own stream (composite_stream) under the next step's front end"}
             if fmt == "u8":
                 out["checksum_rgb8_host"] = int(last["rgb8"].long().sum())
             else:
@@ -461,7 +494,7 @@ def run_ours(args):
                    "outputs": "colour f32 CHW + depth f32 (+ uint8 HWC in e2e); the `radii` output of the reference API "
                               "(205 MB per step, ~0.05 ms) is not requested in the loop (want_radii=False)"},
         "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e, "roofline": roofline,
-        "fast_composite_variant": fast_variant,
+        "fast_composite_variant": fast_variant, "pipelined_variant": pipelined_variant,
         "metrics_allgather": {"per_rank": gathered, "fields": ["steps", "seconds", "checksum_x", "checksum_rgb", "episodes_succeeded", "frames_passed"]},
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # timed on rank 0 at N=1 only
@@ -568,25 +601,34 @@ def run_reference(args):
     rasterizer called once per env, as the reference's env loop would (one render + one blocking
     read-back per call).  Bounded sample: ref_envs environments per step."""
     rank, world, local = dist_env()
-    if rank != 0:
-        return None
     import r2s_testutil as util
     import ref_raster
     from oracle import physics_ref
     from real2sim_eval_b200 import synth
 
     if not ref_raster.available():
-        return {"impl": "reference", "unavailable": "oracle/_ref/libref_raster.so missing (build needs /root/reference)"}
+        return {"impl": "reference", "unavailable": "oracle/_ref/libref_raster.so missing (build needs /root/reference)"} \
+            if rank == 0 else None
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    cores = os.cpu_count() or 1
-    omp_threads = physics_ref.set_threads(cores)     # torchrun exports OMP_NUM_THREADS=1: ask for the host's cores
-    n = args.ref_envs or min(cores, 64)
+    # N > 1: one reference process per GPU, as the reference's own multi-GPU driver runs it
+    # (experiments/eval_policy_parallel.py:266-279: multiprocessing.Pool, episode i -> GPU i % n): every rank steps its
+    # share of the sample with its share of the host threads and its own GPU for the rasterizer; gloo carries the
+    # barrier and the per-rank times.
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("gloo")
+    cores_total = os.cpu_count() or 1
+    cores = max(1, cores_total // world)
+    omp_threads = physics_ref.set_threads(cores)     # torchrun exports OMP_NUM_THREADS=1: ask for this rank's share
+    n_total = args.ref_envs or min(cores_total, 64)
+    n = max(1, n_total // world)
     W, H = args.res
     P = args.gaussians
     scene = {"rope": synth.make_rope, "sloth": synth.make_sloth, "tblock": synth.load_tblock}[args.scene]()
     g = synth.make_gripper(center=(float(scene.x[:, 0].mean()), float(scene.x[:, 1].mean()), 0.004), gap=0.03)
-    envs = _oracle_envs(scene, n, args.substeps, 1234, mesh=util.gripper_mesh_dict(g))
+    envs = _oracle_envs(scene, n, args.substeps, 1234, offset=rank * n, mesh=util.gripper_mesh_dict(g))
     tables = synth.gripper_motion(g, args.substeps, 5e-5, eef_vel=(0.02, 0.0, -0.01))
     for o in envs:
         o.set_mesh_interactive(*tables)
@@ -594,7 +636,7 @@ def run_reference(args):
     gen = torch.Generator(device=dev)
     scenes_t, cams = [], []
     lo, hi = torch.tensor([-0.1, -0.6, 0.0], device=dev), torch.tensor([1.1, 0.6, 0.6], device=dev)
-    for e in range(n):
+    for e in range(rank * n, rank * n + n):
         gen.manual_seed(1234 + 7 * e + 1)
         means = lo + (hi - lo) * torch.rand((P, 3), device=dev, generator=gen)
         scales = torch.exp(np.log(0.006) + 0.5 * torch.randn((P, 3), device=dev, generator=gen))
@@ -630,30 +672,43 @@ def run_reference(args):
     sampler.start()
     time.sleep(1.0)
     sampler.mark()
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         rendered = step()
     dt = time.perf_counter() - t0
     clocks = sampler.stop()
-    value = n * args.steps / dt
+    if dist is not None:                      # whole job = all ranks' envs over the slowest rank's time
+        tt = torch.tensor([dt], dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    value = world * n * args.steps / dt
     # split for the record (one more untimed step)
     t1 = time.perf_counter()
     for o in envs:
         o.update_collision_graph()
     physics_ref.step_batch(envs)
     t_phys = time.perf_counter() - t1
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return None
     return {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"{args.scene} PhysTwin, bounded sample of {n} envs per step (of {args.envs}), "
+        "config": {"workload": f"{args.scene} PhysTwin, bounded sample of {world * n} envs per step (of {world * args.envs}), "
                                f"{args.substeps} substeps/step, one {W}x{H} render of {P} Gaussians per env",
-                   "envs_per_step": n, "substeps": args.substeps, "resolution": [W, H], "gaussians_per_env": P,
+                   "envs_per_step": world * n, "reference_processes": world, "host_threads_per_process": cores,
+                   "substeps": args.substeps, "resolution": [W, H], "gaussians_per_env": P,
                    "instances_last_step": int(rendered)},
         "clocks": clocks, "gpu_launches": 0,
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port+reference",
-                         "sample": f"{n} envs per step: physics = oracle/physics_ref.c (CPU restatement of the Warp "
-                                   f"kernels; warp-lang not installable) on {cores} host threads, render = unmodified "
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores * world, "kind": "port+reference",
+                         "sample": f"{world * n} envs per step over {world} process(es): physics = oracle/physics_ref.c (CPU "
+                                   f"restatement of the Warp kernels, pinned to the reference's kernel source; warp-lang "
+                                   f"not installable) on {cores} host threads per process, render = unmodified "
                                    f"reference CUDA rasterizer (oracle/_ref) once per env with its blocking read-back",
                          "physics_s_per_step": round(t_phys, 4), "omp_threads": omp_threads},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

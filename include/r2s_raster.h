@@ -78,6 +78,11 @@ typedef struct r2s_raster_args {
                                   bit-identical to the reference build.  R2S_COMPOSITE_FAST (1): log2(e) folded into
                                   the staged conic and ex2.approx -- within the 1e-4 relative contract, not bitwise */
     int32_t pad0_;
+    void* composite_stream;    /* NULL: every kernel runs on the stream passed to r2s_raster_forward.  Otherwise the
+                                  compositing kernel is enqueued on THIS stream, ordered after the sort by an event:
+                                  the binning kernels (memory / latency-bound) of the next batch of views can then run
+                                  under the compositing (issue-bound) of this one.  The caller orders whatever reuses
+                                  the workspace or reads the images after this stream */
 } r2s_raster_args;
 #define R2S_COMPOSITE_PRECISE 0
 #define R2S_COMPOSITE_FAST 1

@@ -51,6 +51,7 @@ class RasterArgs(C.Structure):  # include/r2s_raster.h: r2s_raster_args
         ("out_color", c_vp), ("out_depth", c_vp), ("radii", c_vp), ("out_rgb8", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_sz), ("max_instances", c_i64),
         ("tanfov_views", c_vp), ("overflow_count", c_vp), ("composite_mode", c_i32), ("pad0_", c_i32),
+        ("composite_stream", c_vp),
     ]
 
 

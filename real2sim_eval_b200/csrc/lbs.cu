@@ -93,19 +93,23 @@ __global__ void lbs_rotation_kernel(const r2s_lbs_args a)
     if (w[i0] < w[i1]) { int s = i0; i0 = i1; i1 = s; }
     if (w[i0] < w[i2]) { int s = i0; i0 = i2; i2 = s; }
     if (w[i1] < w[i2]) { int s = i1; i1 = i2; i2 = s; }
-    const float s1 = sqrtf(fmaxf(w[i0], 0.0f)), s2 = sqrtf(fmaxf(w[i1], 0.0f));
+    // singular values as |F v|, not as roots of the eigenvalues of F^T F: the latter carry absolute noise of
+    // ~sqrt(eps) * s1, which would count an exactly rank-1 F (collinear bone neighbourhoods) as rank 2, while
+    // |F v2| is good to ~eps * s1 -- the accuracy class of the SVD torch.linalg.matrix_rank runs
+    float v1[3] = {V[0][i0], V[1][i0], V[2][i0]}, v2[3] = {V[0][i1], V[1][i1], V[2][i1]}, v3[3];
+    float u1[3], u2[3], u3[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        u1[r] = F[r][0] * v1[0] + F[r][1] * v1[1] + F[r][2] * v1[2];
+        u2[r] = F[r][0] * v2[0] + F[r][1] * v2[1] + F[r][2] * v2[2];
+    }
+    const float s1 = sqrtf(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
+    const float s2 = sqrtf(u2[0] * u2[0] + u2[1] * u2[1] + u2[2] * u2[2]);
     // torch.linalg.matrix_rank: singular values above sigma_max * max(m, n) * eps count
     const float tol = s1 * 3.0f * 1.1920929e-07f;
     const bool rank_ok = s2 > tol && s1 > 0.0f;
     float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f};
     if (rank_ok) {
-        float v1[3] = {V[0][i0], V[1][i0], V[2][i0]}, v2[3] = {V[0][i1], V[1][i1], V[2][i1]}, v3[3];
-        float u1[3], u2[3], u3[3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            u1[r] = F[r][0] * v1[0] + F[r][1] * v1[1] + F[r][2] * v1[2];
-            u2[r] = F[r][0] * v2[0] + F[r][1] * v2[1] + F[r][2] * v2[2];
-        }
         float l = rsqrtf(u1[0] * u1[0] + u1[1] * u1[1] + u1[2] * u1[2]);
         u1[0] *= l; u1[1] *= l; u1[2] *= l;
         const float d = u1[0] * u2[0] + u1[1] * u2[1] + u1[2] * u2[2];

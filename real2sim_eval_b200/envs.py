@@ -256,12 +256,14 @@ class BatchedEnv:
             out[:, s] = cur
         return out.astype(np.float32)
 
-    def step(self, motion=None, out=None, link_pose=None, command=None):
+    def step(self, motion=None, out=None, link_pose=None, command=None, composite_stream=None):
         """One frame for every env: [end-effector step ->] collision graph -> substeps -> LBS -> robot links -> render.
         `command`: device tensors (eef_xyz, eef_vel, eef_rot, eef_rot_vel, gripper_openness) -- the per-substep
         tables and the grasp hysteresis are then made on the device (r2s_eef_forward); or
         `motion`: ready-made device tables (interp_pts, interp_center, dyn_vel, dyn_omega); or neither.
         `link_pose`: [E,L,4,4] device tensor of the robot's FK link poses for this frame, or None (robot kept).
+        `composite_stream`: a torch stream for the compositing kernel (see r2s_raster_args.composite_stream): the images
+        are complete on THAT stream; everything else of the step runs on the current stream.
         `out`: optional (color, depth[, rgb8]) device tensors to render into (double buffering); rgb8 is
         the [B,H,W,3] uint8 image the reference's evaluation loop builds on the host
         (experiments/eval_policy.py:248), written here by the compositing kernel."""
@@ -287,7 +289,7 @@ class BatchedEnv:
                             tanfovy=self.tanfovy, shs=self.shs, scales=self.scales, rotations=self.rotations,
                             sh_degree=0, z_threshold=0.05, views_per_scene=c.cameras,
                             max_instances=self.max_instances, out_color=color, out_depth=depth,
-                            want_radii=False, out_rgb8=rgb8, fast=c.fast_composite)
+                            want_radii=False, out_rgb8=rgb8, fast=c.fast_composite, composite_stream=composite_stream)
         self.frame += 1
         return color, depth
 

@@ -69,6 +69,7 @@ class BatchedRasterizer:
         # sticky device counter: +1 for every forward whose instance lists overflowed the workspace (that frame
         # holds background only); read with overflows() when convenient -- no per-frame synchronisation
         self.overflow_count = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._composited = None     # event after the last compositing kernel launched on a separate stream
 
     # ---- workspace
     def reserve(self, B, P, W, H, max_instances):
@@ -86,7 +87,7 @@ class BatchedRasterizer:
                 shs=None, colors_precomp=None, scales=None, rotations=None, cov3D_precomp=None, sh_degree=0,
                 scale_modifier=1.0, z_threshold=0.05, prefiltered=False, views_per_scene=1,
                 max_instances=None, out_color=None, out_depth=None, radii=None, want_radii=True, out_rgb8=None,
-                fast=False):
+                fast=False, composite_stream=None):
         """tanfovx / tanfovy: floats shared by every view, or per-view sequences / tensors of length B (the
         reference builds one settings tuple per camera, transform_utils.py:17-30).  fast=True selects the
         ex2.approx compositing variant (within the 1e-4 relative contract, not bit-identical)."""
@@ -132,6 +133,13 @@ class BatchedRasterizer:
         a.scale_modifier, a.tanfovx, a.tanfovy, a.z_threshold = scale_modifier, float(tanfovx), float(tanfovy), z_threshold
         a.tanfov_views, a.overflow_count = _ptr(tanfov_views), _ptr(self.overflow_count)
         a.composite_mode = 1 if fast else 0
+        cur = torch.cuda.current_stream(dev)
+        if composite_stream is not None:
+            # the compositing kernel of the previous forward on this workspace may still be reading the lists and
+            # records this forward rewrites: order this forward's binning after it
+            if self._composited is not None:
+                cur.wait_event(self._composited)
+            a.composite_stream = C.c_void_p(composite_stream.cuda_stream)
         a.means3D, a.scales, a.rotations, a.opacities = _ptr(means3D), _ptr(scales), _ptr(rotations), _ptr(opacities)
         a.shs, a.colors_precomp, a.cov3D_precomp = _ptr(shs), _ptr(colors_precomp), _ptr(cov3D_precomp)
         a.viewmatrix, a.projmatrix, a.campos, a.bg = _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos), _ptr(bg)
@@ -143,6 +151,9 @@ class BatchedRasterizer:
         a.workspace, a.workspace_bytes, a.max_instances = _ptr(self.ws), self.ws.numel(), self.max_instances
         with torch.cuda.device(dev):
             _lib.check(self.lib.r2s_raster_forward(C.byref(a), _stream_ptr(dev)), "r2s_raster_forward")
+        if composite_stream is not None:
+            self._composited = torch.cuda.Event()
+            self._composited.record(composite_stream)
         self._keep = (means3D, opacities, shs, colors_precomp, scales, rotations, cov3D_precomp, viewmatrix,
                       projmatrix, campos, bg, tanfov_views)
         return out_color, radii, out_depth

@@ -63,6 +63,32 @@ def test_batched_envs_and_rank_deficient_env():
         assert np.abs(out[e, :n_obj] - want).max() <= TOL, e
 
 
+def test_exactly_collinear_chain_is_rank_one():
+    """a thin chain whose bone neighbourhoods are exactly collinear along a GENERIC direction, stretched
+    along itself: every F is rank 1 to rounding (s2 / s1 ~ 3e-8; numpy and torch both report rank 1 for all bones), so
+    the reference ends with the identity for every bone.  Singular values taken from the eigenvalues of F^T F carry
+    ~sqrt(eps) * s1 of noise and called these rank 2; |F v2| does not."""
+    import torch
+    from real2sim_eval_b200.lbs import BatchedLBS
+    n, n_obj = 300, 500
+    d = np.array([1.0, 2.0, 3.0]) / np.sqrt(14.0)
+    base = (np.array([0.3, -0.2, 0.1]) + np.outer(np.arange(n) * 0.004, d)).astype(np.float32)
+    rel = lbs_ref.knn_relations(base, 8)
+    motions = np.outer(0.0005 * np.arange(n), d).astype(np.float32)
+    _, ok = lbs_ref.bone_rotations(base, motions, rel)
+    assert not ok, "the reference's rank test (numpy SVD) finds rank-1 bones"
+    rng = np.random.default_rng(9)
+    pts = (base[rng.integers(0, n, n_obj)] + rng.normal(0, 0.002, (n_obj, 3))).astype(np.float32)
+    w, wi = lbs_ref.knn_weights(base, pts, 16)
+    pad = lambda a: torch.tensor(np.concatenate([a, np.zeros_like(a[..., :1])], -1)[None]).cuda().contiguous()
+    lbs = BatchedLBS(1, n, n_obj, n_obj, rel, w, wi)
+    m = torch.tensor(pts[None]).cuda()
+    lbs.forward(pad(base), pad(base + motions), m)
+    assert lbs.rank_flags.cpu().numpy().tolist() == [0]
+    want = lbs_ref.interpolate_motions(base, motions, rel, pts, w, wi)      # identity rotations
+    assert np.abs(m[0].cpu().numpy() - want).max() <= TOL
+
+
 def test_dropin_rejects_the_quat_path():
     import torch
     from real2sim_eval_b200.lbs import interpolate_motions

@@ -5,12 +5,17 @@
  * kywind/real2sim-eval, kernel by kernel.  Only tests/, __graft_entry__.smoke()
  * and bench.py's cpu_baseline / --impl reference legs may load this file.
  *
- * PARITY UNPINNED: the reference physics executes only through warp-lang 1.7.0
- * (not installable offline) and the reference ships no step-transition golden
- * vectors; this restatement is pinned by analytic known-answer tests and by the
- * shipped T-block rest state only (tests/test_oracle_physics.py).  The three
- * Warp built-ins it depends on (HashGrid, Mesh closest point, winding number)
- * are restated from their published algorithm; see the notes at each function.
+ * PINNING.  The reference physics executes only through warp-lang 1.7.0 (not installable offline), but its
+ * kernel bodies are plain Python: oracle/warp_exec.py interprets the warp surface they use and runs the
+ * reference's UNMODIFIED sim/physics/spring_mass_warp.py (and, in tests/test_oracle_reference_stack.py, the
+ * unmodified phystwin.py on top of it) on the CPU.  tests/golden/phys_*.npz hold its outputs on nine seeded
+ * scenarios (tests/golden/make_physics_golden.py); tests/test_oracle_physics_golden.py requires this file to
+ * reproduce them BIT FOR BIT (positions, velocities, per-substep intermediates, candidate rows, resting pairs,
+ * per-face contact forces).  Pinned that way: every kernel's arithmetic and step()'s ordering / aliasing.
+ * STILL UNPINNED: the three Warp built-ins whose code lives in warp-lang's native library (HashGrid cell
+ * arithmetic / iteration order, the mesh closest-point query and its face ties, the winding-number sign) --
+ * restated here and in warp_exec.py from their published algorithm; see the notes at each function.
+ * Analytic known-answer tests and the shipped T-block rest state stay in tests/test_oracle_physics.py.
  *
  * Reference (all file:line relative to /root/reference/):
  *   sim/physics/spring_mass_warp.py   ("SMW")

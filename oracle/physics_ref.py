@@ -1,5 +1,5 @@
-"""ctypes front-end of oracle/physics_ref.c (TEST INFRASTRUCTURE; parity unpinned
-against warp-lang, see the C file's header).  Mirrors the reference's
+"""ctypes front-end of oracle/physics_ref.c (TEST INFRASTRUCTURE; pinned bit for bit to the reference's own
+kernel source executed under oracle/warp_exec.py -- the three Warp built-ins stay restated, see the C file's header).  Mirrors the reference's
 SpringMassSystemWarp surface (sim/physics/spring_mass_warp.py:477-995) closely
 enough that tests read like calls into the reference."""
 from __future__ import annotations

@@ -143,3 +143,22 @@ def test_pusher_env_driven_by_commands_matches_the_oracles():
     assert np.abs(o.x - o_free.x).max() > 1e-4, "the rod must push the block"
     assert float(env.eef.current_openness[e]) == 1.0
     assert torch.isfinite(env.color).all()
+
+
+def test_success_window_numbers_frames_like_the_reference_pickles():
+    """the reference saves state/{cnt:06d}.pkl BEFORE env.step (experiments/eval_policy.py:209-225), so file
+    k holds the state after k steps and the success scripts count files k >= start.  BatchedEnv must book the state a
+    step produces as frame (steps so far), not (steps so far - 1): with start_frame 3 and a T-block resting on its
+    target, five steps give 3 hits (files 3, 4, 5) -- the episode rule of oracle/metrics_ref.py."""
+    from oracle import metrics_ref
+    from real2sim_eval_b200.envs import BatchedEnv, EnvBatchConfig
+    cfg = EnvBatchConfig(scene="tblock", E=1, W=64, H=64, n_substeps=4, P=2000, gripper=False, pusher=False,
+                         success_start_frame=3)
+    env = BatchedEnv(cfg, "cuda")
+    env.success.target.copy_(env.x_init[0])            # the block rests on its target: every frame passes
+    for _ in range(5):
+        env.step()
+    succ, hits = env.success.result()
+    want = metrics_ref.episode_rule([True] * 6, start_frame=3)[5][0]      # files 0..5, file 0 is the pre-step state
+    assert want == 3 and int(hits[0]) == want and not succ.any()
+    env.check()

@@ -59,7 +59,8 @@ typedef struct r2s_raster_args {
     /* outputs (caller-owned) */
     float* out_color; /* [B,3,H,W] */
     float* out_depth; /* [B,1,H,W] */
-    int32_t* radii;   /* [B,P] or NULL */
+    int32_t* radii;   /* [B,P] or NULL; with NULL the workspace's `radii` / `tiles_touched` arrays are not written
+                         either (no kernel reads them; 8 B per Gaussian of HBM traffic) */
     uint8_t* out_rgb8; /* [B,H,W,3] or NULL: the host-side image format of the reference's evaluation loop,
                           (clamp(color, 0, 1) * 255) truncated to uint8, HWC (gs_renderer.py:949 +
                           experiments/eval_policy.py:248), written by the same kernel as out_color */

@@ -159,6 +159,34 @@ def write_phystwin_assets(tmp, case, scene):
                f"{tmp}/experiments/{case}/train/best_0.pth")
 
 
+def stack_scenario(use_pusher, frames=3):
+    """The closed-loop scenario of drive_and_compare as plain arrays: what tests/golden/make_stack_golden.py feeds the
+    full reference stack and tests/test_gpu_env.py feeds the device path.  Returns dict(scene, table, center, meshes,
+    commands=[(xyz, vel, rot, rvel, openness)], dt, S)."""
+    from real2sim_eval_b200 import synth
+    sc = synth.make_rope()
+    if use_pusher:
+        center = (0.5, 0.03, 0.004)
+        tool = synth.make_pusher(center, n_circ=12, n_len=6)
+        table = np.repeat(tool.verts[None], 101, 0).astype(np.float32)
+        meshes = [(tool.verts, tool.faces)]
+    else:
+        center = (0.5, 0.0, 0.004)
+        table = synth.gripper_opening_table(center)
+        g = synth.make_gripper(center, gap=0.08)
+        half, fh = len(g.verts) // 2, len(g.faces) // 2
+        meshes = [(g.verts[:half], g.faces[:fh]), (g.verts[half:], g.faces[fh:] - half)]
+    dt, S = 5e-5, 20
+    xyz = np.asarray(center, np.float32)
+    cmds = []
+    for f in range(frames):
+        vel = np.float32([0.0, -0.6, 0.0]) if use_pusher else np.float32([0.0, 0.0, -0.25])
+        rvel = np.float32([0.0, 0.0, 0.3])
+        cmds.append((xyz.copy(), vel, synth.EEF_ROT_DOWN.copy(), rvel, np.float32(0.25 - 0.1 * f)))
+        xyz = (xyz + vel * np.float32(dt * S)).astype(np.float32)
+    return dict(scene=sc, table=table, center=np.asarray(center, np.float32), meshes=meshes, commands=cmds, dt=dt, S=S)
+
+
 def drive_and_compare(pt, dev, use_pusher, tmp, frames=3):
     """Construct the reference's SpringMassDynamicsModule on the synthetic rope (whatever simulator class the loaded
     module is bound to) and step it `frames` times; the same commands go through oracle/eef_ref.py + the C physics
@@ -202,7 +230,7 @@ def drive_and_compare(pt, dev, use_pusher, tmp, frames=3):
     xyz = np.asarray(center, np.float32)
     cur, grasped = None, False
     faces = None if use_pusher else eef_ref.force_faces(o.mesh_map)
-    errs = []
+    errs, xs = [], []
     o_free = util.oracle_from_scene(sc, S, gather_order=False)   # the same rope without any tool
     for f in range(frames):
         vel = np.float32([0.0, -0.6, 0.0]) if use_pusher else np.float32([0.0, 0.0, -0.25])
@@ -220,9 +248,11 @@ def drive_and_compare(pt, dev, use_pusher, tmp, frames=3):
         o.set_mesh_interactive(e["interp_pts"], e["interp_center"], e["dyn_vel"], e["dyn_omega"])
         o.step()
         o_free.update_collision_graph(); o_free.step()
-        errs.append(np.abs(x_ref.detach().cpu().numpy() - o.x).max(1))
+        xs.append(x_ref.detach().cpu().numpy().copy())
+        errs.append(np.abs(xs[-1] - o.x).max(1))
         if not use_pusher:
             assert abs(float(mod.current_openness) - cur) < 1e-7
         xyz = (xyz + vel * np.float32(cfg.dt * S)).astype(np.float32)
     assert np.abs(o.x - o_free.x).max() > 1e-4, "the tool must have moved the rope"
+    mod._r2s_x_frames = xs
     return mod, errs, o

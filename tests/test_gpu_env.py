@@ -1,5 +1,7 @@
 """GPU tests of the batched env step (physics -> re-bind -> render) at the shapes of BASELINE configs 3
 and 4: two cameras per env sharing one Gaussian set, the sloth and T-block particle counts."""
+import os
+
 import numpy as np
 import pytest
 
@@ -162,3 +164,53 @@ def test_success_window_numbers_frames_like_the_reference_pickles():
     want = metrics_ref.episode_rule([True] * 6, start_frame=3)[5][0]      # files 0..5, file 0 is the pre-step state
     assert want == 3 and int(hits[0]) == want and not succ.any()
     env.check()
+
+
+@pytest.mark.parametrize("tool", ["gripper", "pusher"])
+def test_device_loop_matches_the_complete_reference_stack(tool):
+    """tests/golden/stack_*.npz: positions returned by the reference's unmodified phystwin.py + spring_mass_warp.py
+    (CPU, under oracle/warp_exec.py; tests/golden/make_stack_golden.py) after each of three closed-loop frames.
+    Here the same commands go through the DEVICE path -- r2s_eef_forward (tables + grasp hysteresis from last
+    frame's finger forces) writing into the physics handle, then r2s_phys_step -- and must land on the reference's
+    positions and grasp state."""
+    import hashlib
+    import torch
+    import phys_cases
+    import ref_harness
+    from real2sim_eval_b200.eef import BatchedEefMotion
+    from real2sim_eval_b200.physics import BatchedSpringMass
+    use_pusher = tool == "pusher"
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"stack_{tool}.npz"))
+    sn = ref_harness.stack_scenario(use_pusher)
+    sc = sn["scene"]
+    assert hashlib.sha256(np.ascontiguousarray(sc.springs).tobytes()).hexdigest() == str(g["springs_sha"])
+    # rest lengths as the reference module makes them (torch.linalg.norm on the float32 cloud, phystwin.py:285-286)
+    pts = torch.tensor(sc.x.astype(np.float64), dtype=torch.float32)
+    spr = torch.tensor(sc.springs.astype(np.int64))
+    rest = torch.linalg.norm(pts[spr[:, 0]] - pts[spr[:, 1]], dim=1).numpy()
+    # (bitwise equal to the golden's on the build box -- rest_sha -- but a host with another SIMD width may round the
+    # last place differently; 1 ulp of a rest length moves positions by ~1e-7 m, far inside the tolerance below)
+    assert np.allclose(rest, sc.rest, rtol=3e-7, atol=0)
+    p = dict(sc.params)
+    if use_pusher:
+        p["collide_eef_fric"] = 0.2
+    phys = BatchedSpringMass(1, sc.springs, rest, num_particles=sc.N, n_substeps=sn["S"], log_spring_Y=sc.log_Y,
+                             masses=sc.mass, use_pusher=use_pusher, precise=True, coll_row_cap=500, **p)
+    phys.set_state(sc.x[None], sc.v[None])
+    m = phys_cases.merged_mesh(dict(meshes=dict(dynamic=sn["meshes"], static=[])))
+    phys.set_mesh(**m)
+    phys.create_resting_case()
+    eef = BatchedEefMotion(1, sn["table"], sn["center"], dt=sn["dt"], n_substeps=sn["S"], use_pusher=use_pusher,
+                           mesh_map=None if use_pusher else m["mesh_map"], phys=phys)
+    t = lambda a: torch.tensor(np.asarray(a, np.float32)[None]).cuda().contiguous()
+    budget = 0.03 if use_pusher else 0.01
+    for f, (xyz, vel, rot, rvel, opn) in enumerate(sn["commands"]):
+        phys.update_collision_graph()
+        eef.forward(t(xyz), t(vel), t(rot), t(rvel), None if use_pusher else t([opn]).reshape(1))
+        phys.step()
+        x = phys.get_state()[0][0].cpu().numpy()
+        dx = np.abs(x - g["x"][f]).max(1)
+        assert (dx > 1e-5).mean() <= budget and dx.max() < 2e-3, f"frame {f}: |dx|max {dx.max()}, {(dx > 1e-5).sum()} particles"
+    if not use_pusher:
+        assert float(eef.current_openness[0]) == pytest.approx(float(g["current_openness"]), abs=1e-7)
+        assert bool(eef.grasped[0]) == bool(g["grasped"])

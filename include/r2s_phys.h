@@ -44,9 +44,10 @@ typedef struct r2s_phys_desc {
     int32_t precise;        /* 1: IEEE sqrt/divide in the reference's expression order (SMW:87-99);
                                0 (default): 1/len by rsqrt + one Newton step and 1/rest precomputed --
                                the same formula to a few ulp, ~2x faster          */
-    int32_t mesh_accel;     /* rigid-tool mesh accelerator: 0 auto (pusher meshes with >= 256 faces whose every
-                               vertex is dynamic), 1 force, -1 off.  Uniform grid in the tool's rest frame +
-                               pseudonormal inside/outside; the tool must move rigidly (PT:462-510)          */
+    int32_t mesh_accel;     /* rigid-tool mesh accelerator: 0 auto (pusher meshes of >= 256 tool faces), 1 force,
+                               -1 off.  Uniform grid in the tool's rest frame + pseudonormal inside/outside; the tool
+                               must move rigidly (PT:462-510) and its faces must come first; static obstacle faces
+                               may follow (they are scanned beside the grid query, SMW:652-676)             */
     int32_t pad0_;
     float dt, dashpot_damping, drag_damping;
     float spring_Y_min, spring_Y_max, collision_dist;

@@ -89,6 +89,7 @@ struct FrameParams {
     float* coll_forces;  // [E][F][3]
     // rigid dynamic mesh accelerator (set when the whole mesh is one rigidly moving tool, e.g. the pusher)
     int accel;                  // 0: brute force over the faces; 1: uniform grid + pseudonormal sign
+    int F_dyn;                  // faces [0, F_dyn) are the rigid tool (gridded); [F_dyn, F) static obstacles (scanned)
     const float* frec;          // [F][24] rest-frame face record: v0 v1 v2 | n | e01 e12 e20 | pad
     const float* vnorm;         // [V][3] angle-weighted vertex pseudonormals
     const int* cell_start;      // [ncell + 1]
@@ -772,9 +773,27 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                     float3 cr;
                     const GridView gv = {p.frec, p.vnorm, p.cell_start, p.cell_tris, p.faces, p.cell_skip, p.gx0, p.gy0, p.gz0, p.gh,
                                          p.gnx, p.gny, p.gnz, p.sign_mode};
-                    if (!mesh_query_grid(gv, qr, 0.02f, s_triq + (tid >> 5) * kTriQueue, qface, cr, qsign)) return false;
-                    qpc = f3(R[0] * cr.x + R[1] * cr.y + R[2] * cr.z + R[9], R[3] * cr.x + R[4] * cr.y + R[5] * cr.z + R[10],
-                             R[6] * cr.x + R[7] * cr.y + R[8] * cr.z + R[11]);
+                    const bool hit_t = mesh_query_grid(gv, qr, 0.02f, s_triq + (tid >> 5) * kTriQueue, qface, cr, qsign);
+                    if (hit_t)
+                        qpc = f3(R[0] * cr.x + R[1] * cr.y + R[2] * cr.z + R[9], R[3] * cr.x + R[4] * cr.y + R[5] * cr.z + R[10],
+                                 R[6] * cr.x + R[7] * cr.y + R[8] * cr.z + R[11]);
+                    if (p.F_dyn == p.F) return hit_t;
+                    // static obstacles beside the tool (the reference keeps both in one BVH, SMW:652-676): their faces are
+                    // scanned by the warp (group kMaxParts of the brute-force query: box pruning, exact winding number over
+                    // the static faces).  The merged query is the nearer of the two hits (ties to the lower face index, i.e.
+                    // the tool), and the merged winding number is the sum of the two meshes': inside either one is inside.
+                    MeshView sm = mesh;
+                    sm.grp = s_grp + 3 * kMaxParts; sm.boxes = s_aabb + 6 * kMaxParts; sm.n_grp = 1;
+                    int sface; float su, sv, ssign;
+                    const bool hit_s = mesh_query_warp(sm, q, 0.02f, 0.6f, p.sign_mode, sface, su, sv, ssign);
+                    if (!hit_t && !hit_s) return false;
+                    const bool inside = (hit_t && qsign < 0.0f) || (hit_s && ssign < 0.0f);
+                    if (hit_s) {
+                        const float3 spc = mesh_eval(sm, sface, su, sv);
+                        const float3 ds = spc - q, dt_ = qpc - q;
+                        if (!hit_t || dot3(ds, ds) < dot3(dt_, dt_)) { qface = sface; qpc = spc; }
+                    }
+                    qsign = inside ? -1.0f : 1.0f;
                     return true;
                 };
                 int face; float sign; float3 pc;
@@ -1195,6 +1214,7 @@ struct r2s_phys {
     int motion_substeps = 0;
     // rigid-tool accelerator
     int accel = 0;
+    int F_dyn = 0;
     float* frec = nullptr;
     float* vnorm = nullptr;
     int* cell_start = nullptr;
@@ -1701,10 +1721,20 @@ int r2s_phys_set_mesh(r2s_phys* h, const float* verts, const int32_t* faces, con
     h->motion_per_env = 0;
     h->motion_substeps = ns;
     // a mesh that is entirely one rigidly moving tool (the pusher: every vertex dynamic) gets the grid accelerator
+    // (static obstacles may follow it: their faces are scanned beside the grid query)
     const int want = h->d.mesh_accel;
-    if (want > 0 || (want == 0 && h->d.use_pusher && n_dyn == V && F >= 256)) {
-        R2S_REQUIRE(n_dyn == V, "r2s_phys_set_mesh: mesh_accel needs a fully dynamic (rigid tool) mesh");
-        if (int rc = build_accel(h, verts, faces, V, F)) return rc;
+    int F_dyn = F;
+    bool tool_first = true;   // dynamic faces are the first F_dyn faces and use only dynamic vertices; the rest are static
+    if (n_dyn < V) {
+        tool_first = h->n_grp == 5 && h->grp[0] == 0 && h->grp[3 * 4 + 1] == F && h->grp[1] == h->grp[3 * 4] &&
+                     h->grp[3 * 1 + 1] == 0 && h->grp[3 * 2 + 1] == 0 && h->grp[3 * 3 + 1] == 0;
+        F_dyn = tool_first ? h->grp[1] : F;
+    }
+    h->F_dyn = F;
+    if (want > 0 || (want == 0 && h->d.use_pusher && tool_first && n_dyn > 0 && F_dyn >= 256)) {
+        R2S_REQUIRE(tool_first && n_dyn > 0, "r2s_phys_set_mesh: mesh_accel needs ONE rigid tool whose faces come first (static faces may follow)");
+        if (int rc = build_accel(h, verts, faces, n_dyn, F_dyn)) return rc;
+        h->F_dyn = F_dyn;
     }
     return configure_launch(h);
 }
@@ -1822,7 +1852,7 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     p.dynvel_stride = pe * 6;
     p.omega_stride = pe * 3;
     p.coll_forces = h->coll_forces;
-    p.accel = h->accel;
+    p.accel = h->accel; p.F_dyn = h->F_dyn;
     p.frec = h->frec; p.vnorm = h->vnorm; p.cell_start = h->cell_start; p.cell_tris = h->cell_tris; p.cell_skip = h->cell_skip;
     p.gx0 = h->grid0[0]; p.gy0 = h->grid0[1]; p.gz0 = h->grid0[2]; p.gh = h->grid_h;
     p.gnx = h->grid_n[0]; p.gny = h->grid_n[1]; p.gnz = h->grid_n[2];

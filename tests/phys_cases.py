@@ -119,7 +119,18 @@ def pusher_tblock():
                  over=dict(collide_eef_fric=0.2))
 
 
-CASES = dict(rope_s10=rope_s10, tblock_s100=tblock_s100, two_ropes_collide=two_ropes_collide,
+def pusher_static_tblock():
+    """The rod pushes the T-block against a STATIC obstacle standing at its far side (mesh_map -1 after the tool's 0):
+    tool and static faces in one merged mesh, as the reference keeps them in one BVH (SMW:636-676)."""
+    c = pusher_tblock()
+    sc = c["scene"]
+    wv, wf = synth.make_finger_mesh(length=0.06, half_w=0.02, half_t=0.03)
+    wall = (wv + np.array([float(sc.x[:, 0].max()) + 0.02 - 0.0005, 0.0, 0.0], np.float32)).astype(np.float32)
+    c["meshes"] = dict(dynamic=c["meshes"]["dynamic"], static=[(wall, wf)])
+    return c
+
+
+CASES = dict(pusher_static_tblock=pusher_static_tblock, rope_s10=rope_s10, tblock_s100=tblock_s100, two_ropes_collide=two_ropes_collide,
              chain_ground=chain_ground, chain_reverse_z=chain_reverse_z, gripper_graze=gripper_graze,
              gripper_inside=gripper_inside, static_and_gripper=static_and_gripper, pusher_tblock=pusher_tblock)
 

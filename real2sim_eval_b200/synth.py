@@ -366,6 +366,23 @@ def make_camera(W: int, H: int, which: str = "side", jitter_seed: int | None = N
     return setup_camera(W, H, k, np.linalg.inv(c2w))
 
 
+def spatial_order(pts: np.ndarray) -> np.ndarray:
+    """Permutation that sorts points along a 30-bit Morton (Z-order) curve of their bounding box: consecutive points are
+    spatial neighbours.  Used to lay the object Gaussians out so that the 32 Gaussians of a warp share most of their
+    bones (the LBS blend then gathers a handful of distinct transforms per warp instead of 32 x 16)."""
+    p = np.asarray(pts, np.float64)
+    lo, hi = p.min(0), p.max(0)
+    q = np.clip(((p - lo) / np.maximum(hi - lo, 1e-12) * 1023.0).astype(np.int64), 0, 1023)
+
+    def spread(v):
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        return (v | (v << 2)) & 0x09249249
+
+    return np.argsort(spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2), kind="stable")
+
+
 @dataclass
 class Gaussians:
     means3D: np.ndarray    # (P,3)

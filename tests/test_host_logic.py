@@ -197,3 +197,26 @@ def test_super_tile_local_rectangle_is_equivalent_to_the_global_one():
     low = (123456 << 12) | (1 | (2 << 3) | (4 << 6) | (3 << 9))
     assert (low & 7, (low >> 3) & 7, (low >> 6) & 7, (low >> 9) & 7, low >> 12) == (1, 2, 4, 3, 123456)
     assert ((1 << 20) - 1) << 12 < (1 << 32), "ids below 2^20 fit above the 12 rectangle bits"
+
+
+def test_bench_config_label_and_numa_binding_are_safe_without_a_gpu():
+    """bench.py helpers: the BASELINE config a command line describes, and the NUMA binding, which must degrade to a
+    report (never raise) on a box without GPUs or sysfs entries."""
+    import types
+    import bench
+    mk = lambda **kw: types.SimpleNamespace(**{**dict(scene="rope", envs=256, res=[512, 512], cameras=1, substeps=10), **kw})
+    assert bench.config_label(mk()) == "BASELINE configs[1]"
+    assert bench.config_label(mk(scene="sloth", envs=64, res=[640, 480], cameras=2)) == "BASELINE configs[2]"
+    assert bench.config_label(mk(envs=128)) == "custom shape"
+    info = bench.bind_to_gpu_numa_node(0)
+    assert info["bound"] is False and ("error" in info or "numa_node" in info)
+
+
+def test_spatial_order_is_a_permutation_that_keeps_neighbours_together():
+    from real2sim_eval_b200 import synth
+    p = np.random.default_rng(0).uniform(0, 1, (2000, 3))
+    o = synth.spatial_order(p)
+    assert sorted(o.tolist()) == list(range(2000))
+    step_sorted = np.linalg.norm(np.diff(p[o], axis=0), axis=1).mean()
+    step_random = np.linalg.norm(np.diff(p, axis=0), axis=1).mean()
+    assert step_sorted < 0.3 * step_random

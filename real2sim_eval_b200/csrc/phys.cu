@@ -858,6 +858,7 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         }
                     }
                 }
+                __syncwarp();   // every lane has read sx[i] / sv[i] (top of this iteration) before lane 0 overwrites them
                 if (lane == 0) integrate_ground(i, next_x, next_v);
             }
         }

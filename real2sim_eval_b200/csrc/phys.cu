@@ -596,11 +596,12 @@ __global__ void __launch_bounds__(1024, 1) frame_kernel(const FrameParams p)
                         float y = rsqrtf(c2);
                         y = y * (1.5f - 0.5f * c2 * y * y);           // Newton step: 1/max(len,1e-6) to ~1 ulp
                         const float dis_len = len2 >= 1e-12f ? len2 * y : sqrtf(len2);
-                        const float3 d = dis * y;
-                        const float3 spring_force = d * (kk * fmaf(dis_len, r, -1.0f));  // r = 1/rest
-                        const float v_rel = dot3(vj - vi, d);
-                        const float3 dashpot = d * (p.dashpot * v_rel);
-                        acc = acc + (spring_force + dashpot);
+                        // F = (k (len / rest - 1) + damp (dv . d)) d with d = dis * y, factored so that the unit vector is
+                        // never formed: one scalar coefficient on dis (9 operations instead of 19)
+                        const float s_coef = kk * fmaf(dis_len, r, -1.0f);               // r = 1/rest
+                        const float v_rel = dot3(vj - vi, dis) * y;
+                        const float coef = fmaf(p.dashpot, v_rel, s_coef) * y;
+                        acc.x = fmaf(coef, dis.x, acc.x); acc.y = fmaf(coef, dis.y, acc.y); acc.z = fmaf(coef, dis.z, acc.z);
                     }
                 }
             }

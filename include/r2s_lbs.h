@@ -39,6 +39,15 @@ typedef struct r2s_lbs_args {
     float* rot_scratch;             /* [E, N, 12] bone transforms [R | new - R old] as three float4 rows;
                                        caller-owned scratch, 16-byte aligned                       */
     int32_t* rank_flags;            /* [E] out: 1 if every bone had rank >= 2, else 0 (identity used) */
+    /* Optional layout hints, all three or none (null = bone transforms stored in bone order).  They change where
+       a bone's transform sits in `rot_scratch` (and in the blend kernel's shared-memory copy), not what is computed:
+       bone i is stored in slot bone_slot[i], and the blend reads row g of `weights_slots` / `weights_by_slot` --
+       the same (bone, weight) pairs as row g of weights_indices / weights, with the bone replaced by its slot and
+       the pairs in any order the caller likes (ascending slot keeps the 32 Gaussians of a warp on neighbouring
+       rows).  The sum over a Gaussian's bones then runs in that order.                                         */
+    const int32_t* bone_slot;       /* [N] a permutation of 0..N-1, shared                          */
+    const int32_t* weights_slots;   /* [n_obj, k_wgt] shared                                        */
+    const float* weights_by_slot;   /* [n_obj, k_wgt] shared                                        */
 } r2s_lbs_args;
 
 /* Two launches on `stream`: per-bone rotations, then the per-Gaussian blend. */

@@ -96,6 +96,7 @@ class LbsArgs(C.Structure):  # include/r2s_lbs.h: r2s_lbs_args
         ("E", c_i32), ("N", c_i32), ("P", c_i32), ("n_obj", c_i32), ("k_rel", c_i32), ("k_wgt", c_i32),
         ("relations", c_vp), ("weights_indices", c_vp), ("weights", c_vp), ("bones4", c_vp), ("bones_new4", c_vp),
         ("means3D", c_vp), ("rot_scratch", c_vp), ("rank_flags", c_vp),
+        ("bone_slot", c_vp), ("weights_slots", c_vp), ("weights_by_slot", c_vp),
     ]
 
 

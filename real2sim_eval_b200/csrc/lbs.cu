@@ -127,7 +127,7 @@ __global__ void lbs_rotation_kernel(const r2s_lbs_args a)
     }
     // bone transform as three float4 rows [R | c], c = new - R old, so that the blend is sum_k w_k (R x + c):
     // algebraically the reference's R (x - old) + motion + old
-    float4* out = reinterpret_cast<float4*>(a.rot_scratch) + (size_t)t * 3;
+    float4* out = reinterpret_cast<float4*>(a.rot_scratch) + ((size_t)e * a.N + (a.bone_slot ? a.bone_slot[i] : i)) * 3;
     out[0] = make_float4(R[0], R[1], R[2], n0.x - (R[0] * o0.x + R[1] * o0.y + R[2] * o0.z));
     out[1] = make_float4(R[3], R[4], R[5], n0.y - (R[3] * o0.x + R[4] * o0.y + R[5] * o0.z));
     out[2] = make_float4(R[6], R[7], R[8], n0.z - (R[6] * o0.x + R[7] * o0.y + R[8] * o0.z));
@@ -158,7 +158,9 @@ __global__ void lbs_blend_kernel(const r2s_lbs_args a, int per_block)
     const float4* b1 = reinterpret_cast<const float4*>(a.bones_new4) + (size_t)e * a.N;
     const int g_end = min(a.n_obj, (int)(blockIdx.x + 1) * per_block);
     const bool vec4 = (a.k_wgt & 3) == 0 && ((reinterpret_cast<uintptr_t>(a.weights_indices) |
-                                              reinterpret_cast<uintptr_t>(a.weights)) & 15) == 0;
+                                              reinterpret_cast<uintptr_t>(a.weights) |
+                                              reinterpret_cast<uintptr_t>(a.weights_slots) |
+                                              reinterpret_cast<uintptr_t>(a.weights_by_slot)) & 15) == 0;
     // `T` is either the shared-memory copy or the global table; the loop is instantiated once per address space
     // (a pointer selected at run time would compile to generic loads, which cost several times an LDS here)
     auto run = [&](const float4* __restrict__ T) {
@@ -166,8 +168,9 @@ __global__ void lbs_blend_kernel(const r2s_lbs_args a, int per_block)
             float* x = a.means3D + ((size_t)e * a.P + g) * 3;
             const float px = x[0], py = x[1], pz = x[2];
             float ox = 0.f, oy = 0.f, oz = 0.f;
-            const int* wi = a.weights_indices + (size_t)g * a.k_wgt;
-            const float* ww = a.weights + (size_t)g * a.k_wgt;
+            // with R: rows of T are addressed by slot (the caller's layout hint) when one is given
+            const int* wi = (use_R && a.weights_slots ? a.weights_slots : a.weights_indices) + (size_t)g * a.k_wgt;
+            const float* ww = (use_R && a.weights_slots ? a.weights_by_slot : a.weights) + (size_t)g * a.k_wgt;
             auto bone = [&](int b, float wk) {
                 float tx, ty, tz;
                 if (use_R) {
@@ -210,6 +213,9 @@ extern "C" int r2s_lbs_forward(const r2s_lbs_args* a, void* stream)
     R2S_REQUIRE(a->relations && a->weights_indices && a->weights && a->bones4 && a->bones_new4 && a->means3D &&
                     a->rot_scratch && a->rank_flags,
                 "r2s_lbs_forward: null pointer");
+    R2S_REQUIRE((a->bone_slot != nullptr) == (a->weights_slots != nullptr) &&
+                    (a->bone_slot != nullptr) == (a->weights_by_slot != nullptr),
+                "r2s_lbs_forward: bone_slot, weights_slots and weights_by_slot go together");
     cudaStream_t st = (cudaStream_t)stream;
     lbs_flag_reset_kernel<<<r2s::ceil_div(a->E, 256), 256, 0, st>>>(a->rank_flags, a->E);
     R2S_LAUNCH_CHECK();

@@ -145,7 +145,8 @@ class BatchedEnv:
         w = 1.0 / (dist.reshape(n_obj, self.K).astype(np.float32) + np.float32(1e-6))
         w = (w / w.sum(1, keepdims=True)).astype(np.float32)
         rel = tree.query(base.x, k=cfg.k_rel + 1)[1][:, 1:]        # gs_renderer.py:195-200 knn_relations
-        self.lbs = BatchedLBS(E, base.N, P, n_obj, rel, w, idx.reshape(n_obj, self.K), device=dev)
+        self.lbs = BatchedLBS(E, base.N, P, n_obj, rel, w, idx.reshape(n_obj, self.K), device=dev,
+                              bone_positions=base.x if cfg.sort_object_gaussians else None)
         self.x_prev4 = torch.empty_like(self.phys.x4)
         # robot scan: rows [n_obj, n_obj + n_robot) of every env, one shared scan, per-env link poses
         self.n_robot = int(P * cfg.robot_frac)

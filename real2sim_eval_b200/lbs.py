@@ -18,10 +18,23 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def slot_layout(bone_positions, weights_indices, weights):
+    """The layout hint of include/r2s_lbs.h from the bones' rest positions: `bone_slot` [N] = rank of each bone along
+    a Morton curve, and per Gaussian the same (bone, weight) pairs with the bone replaced by its slot, ascending."""
+    from .synth import spatial_order
+    pos = np.asarray(bone_positions, np.float64).reshape(-1, 3)
+    slot = np.empty(pos.shape[0], np.int64)
+    slot[spatial_order(pos)] = np.arange(pos.shape[0])
+    ws = slot[np.asarray(weights_indices, np.int64)]
+    order = np.argsort(ws, axis=1, kind="stable")
+    return (slot.astype(np.int32), np.take_along_axis(ws, order, 1).astype(np.int32),
+            np.take_along_axis(np.asarray(weights, np.float32), order, 1))
+
+
 class BatchedLBS:
     """Shared relations / weights (one PhysTwin), per-environment bones and Gaussians."""
 
-    def __init__(self, E, N, P, n_obj, relations, weights, weights_indices, device="cuda"):
+    def __init__(self, E, N, P, n_obj, relations, weights, weights_indices, device="cuda", bone_positions=None):
         self.device = dev = torch.device(device)
         if dev.type != "cuda":
             raise _lib.R2SError("BatchedLBS needs a CUDA device: there is no CPU path")
@@ -33,6 +46,14 @@ class BatchedLBS:
         self.weights_indices = as_t(weights_indices, torch.int32)
         assert self.relations.shape[0] == self.N and self.weights.shape == self.weights_indices.shape
         assert self.weights.shape[0] == self.n_obj
+        # layout hint (r2s_lbs.h): with the bones' rest positions known, their transforms are stored along a Morton
+        # curve and every Gaussian lists its bones by ascending slot, so the Gaussians of a warp (themselves laid
+        # out spatially by the caller) read neighbouring 48-byte rows of shared memory instead of 32 random ones
+        self.bone_slot = self.weights_slots = self.weights_by_slot = None
+        if bone_positions is not None and self.n_obj > 0:
+            slot, ws, wbs = slot_layout(bone_positions, self.weights_indices.cpu().numpy(), self.weights.cpu().numpy())
+            self.bone_slot, self.weights_slots = as_t(slot, torch.int32), as_t(ws, torch.int32)
+            self.weights_by_slot = as_t(wbs, torch.float32)
         self.rot = torch.empty((self.E, self.N, 12), dtype=torch.float32, device=dev)
         self.rank_flags = torch.ones(self.E, dtype=torch.int32, device=dev)
 
@@ -46,6 +67,7 @@ class BatchedLBS:
         a.relations, a.weights_indices, a.weights = _ptr(self.relations), _ptr(self.weights_indices), _ptr(self.weights)
         a.bones4, a.bones_new4, a.means3D = _ptr(bones4), _ptr(bones_new4), _ptr(means3D)
         a.rot_scratch, a.rank_flags = _ptr(self.rot), _ptr(self.rank_flags)
+        a.bone_slot, a.weights_slots, a.weights_by_slot = _ptr(self.bone_slot), _ptr(self.weights_slots), _ptr(self.weights_by_slot)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.r2s_lbs_forward(C.byref(a), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)),
                        "r2s_lbs_forward")

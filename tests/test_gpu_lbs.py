@@ -32,8 +32,11 @@ def test_cuda_matches_reference_golden(path):
     assert np.abs(out - d["out"]).max() <= TOL
 
 
-def test_batched_envs_and_rank_deficient_env():
-    """E = 3 environments sharing relations / weights: env 1 has a collinear bone cluster AFTER..BEFORE the frame, so
+@pytest.mark.parametrize("slots", [False, True], ids=["bone-order", "morton-slots"])
+def test_batched_envs_and_rank_deficient_env(slots):
+    """(slots: the layout hint of r2s_lbs.h -- bone transforms stored along a Morton curve, each Gaussian's bones
+    listed by ascending slot; same sums in another order, and the identity fallback still reads the bones by index.)
+    E = 3 environments sharing relations / weights: env 1 has a collinear bone cluster AFTER..BEFORE the frame, so
     the reference rule gives it the identity rotation for every bone; envs 0 and 2 are regular."""
     import torch
     from real2sim_eval_b200.lbs import BatchedLBS
@@ -51,7 +54,8 @@ def test_batched_envs_and_rank_deficient_env():
     means[:, :n_obj] = pts[None] + (bones - base[None]).mean(1, keepdims=True)
     means[:, n_obj:] = 7.0
     pad = lambda a: torch.tensor(np.concatenate([a, np.zeros_like(a[..., :1])], -1)).cuda().contiguous()
-    lbs = BatchedLBS(3, n, P, n_obj, rel, w, wi)
+    lbs = BatchedLBS(3, n, P, n_obj, rel, w, wi, bone_positions=base if slots else None)
+    assert (lbs.bone_slot is not None) == slots
     m = torch.tensor(means).cuda()
     lbs.forward(pad(bones), pad(bones + motions), m)
     flags = lbs.rank_flags.cpu().numpy().tolist()

@@ -220,3 +220,29 @@ def test_spatial_order_is_a_permutation_that_keeps_neighbours_together():
     step_sorted = np.linalg.norm(np.diff(p[o], axis=0), axis=1).mean()
     step_random = np.linalg.norm(np.diff(p, axis=0), axis=1).mean()
     assert step_sorted < 0.3 * step_random
+
+
+def test_lbs_slot_layout_keeps_every_bone_weight_pair():
+    """The LBS layout hint (include/r2s_lbs.h: bone_slot / weights_slots / weights_by_slot) only moves data: the slots
+    are a permutation, every Gaussian keeps its (bone, weight) pairs, rows ascend, and neighbouring bones get
+    neighbouring slots; the oracle's blend over the re-ordered pairs is the same sum to rounding."""
+    from oracle import lbs_ref
+    from real2sim_eval_b200.lbs import slot_layout
+    rng = np.random.default_rng(3)
+    n, n_obj, k = 500, 300, 16
+    base = rng.uniform(0, 0.2, (n, 3)).astype(np.float32)
+    pts = (base[rng.integers(0, n, n_obj)] + rng.normal(0, 0.003, (n_obj, 3))).astype(np.float32)
+    w, wi = lbs_ref.knn_weights(base, pts, k)
+    slot, ws, wbs = slot_layout(base, wi, w)
+    assert sorted(slot.tolist()) == list(range(n))
+    assert (np.diff(ws, axis=1) >= 0).all()
+    inv = np.empty(n, np.int64); inv[slot] = np.arange(n)
+    for g in range(n_obj):
+        assert sorted(zip(inv[ws[g]].tolist(), wbs[g].tolist())) == sorted(zip(wi[g].tolist(), w[g].tolist()))
+    spread = lambda rows: np.mean(rows.max(1) - rows.min(1))
+    assert spread(ws) < 0.5 * spread(np.asarray(wi)), "a Gaussian's bones sit closer together in slot order"
+    rel = lbs_ref.knn_relations(base, 8)
+    motions = (0.02 * np.sin(30 * base[:, [1, 2, 0]])).astype(np.float32)
+    a = lbs_ref.interpolate_motions(base, motions, rel, pts, w, wi)
+    b = lbs_ref.interpolate_motions(base, motions, rel, pts, wbs, inv[ws])
+    assert np.abs(a - b).max() < 1e-6

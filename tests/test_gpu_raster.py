@@ -355,6 +355,32 @@ def test_matches_unmodified_reference_cuda(W, H, P, seed, deg):
     assert bad.mean() <= 0.05 and np.abs(oc - rc).max() <= 2e-2, (bad.mean(), np.abs(oc - rc).max())
 
 
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "..", "oracle", "_ref", "libref_raster.so")),
+                    reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_non_positive_tiny_and_large_opacities_match_reference():
+    """The compositing kernel applies expf's power-of-two factor on the exponent field of opacity * r, which is exact
+    only for a positive product that does not underflow.  Opacities outside (0, 1] -- negative, zero, denormal-small,
+    above one -- must still give the reference's image: the reference skips alpha < 1/255 and clamps at 0.99."""
+    import ref_raster
+    W, H, P = 96, 96, 3000
+    g = _util.small_gaussians(11, P)
+    op = g["opacities"].copy()
+    rng = np.random.default_rng(5)
+    kind = rng.integers(0, 8, P)
+    op[kind == 0] = -0.7
+    op[kind == 1] = 0.0
+    op[kind == 2] = 1e-30
+    op[kind == 3] = 3.5
+    op[kind == 4] = 1.0 / 255.0
+    g = dict(g, opacities=op.astype(np.float32))
+    cam = _util.make_test_camera(W, H)
+    r, color, radii, depth, total, _ = _run_cuda(g, cam, bg=(0.3, 0.1, 0.2))
+    rc, rr, rd, n = _assert_lists_equal_reference(r, g, cam, bg=(0.3, 0.1, 0.2), total=total)
+    assert total == n and np.array_equal(radii, rr)
+    assert np.array_equal(color, rc), f"colour not bit-identical: {(color != rc).sum()} values"
+    assert np.array_equal(depth, rd), f"depth not bit-identical: {(depth != rd).sum()} values"
+
+
 def test_golden_fixtures_from_reference():
     files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "raster_*.npz")))
     if not files:

@@ -246,3 +246,25 @@ def test_lbs_slot_layout_keeps_every_bone_weight_pair():
     a = lbs_ref.interpolate_motions(base, motions, rel, pts, w, wi)
     b = lbs_ref.interpolate_motions(base, motions, rel, pts, wbs, inv[ws])
     assert np.abs(a - b).max() < 1e-6
+
+
+def test_ncu_sass_tool_summarises_a_source_page(tmp_path):
+    """tools/ncu_sass.py on a hand-made `ncu --page source --csv --print-source sass` excerpt: opcode mix weighted by
+    executions (predicated instructions counted under their opcode), the bulk-copy / mbarrier list, the hot-loop window."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = '"Address","Source","Warp Stall Sampling (All Samples)","Warp Stall Sampling (Not-issued Samples)","# Samples","Instructions Executed"'
+    rows = [("LDC R1, c[0x0][0x37c]", 10, 1), ("UBLKCP.S.G [UR8], [UR4], UR6", 4, 2), ("FFMA R1, R2, R3, R4", 600, 5),
+            ("@!P0 BRA 0x10", 100, 7), ("MUFU.EX2 R5, R5", 200, 9), ("FMUL R5, R5, R6", 90, 3)]
+    src = tmp_path / "sass.csv"
+    src.write_text('"Kernel Name","k",\n' + hdr + "\n" +
+                   "".join(f'"0x{16 * i:x}","      {s}","{n}","0","{n}","{ex}"\n' for i, (s, ex, n) in enumerate(rows)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_sass.py"), str(src), "--nth", "1", "--before", "1",
+                          "--window", "2"], capture_output=True, text=True, check=True).stdout
+    assert "total warp instructions 1,004, stall samples 27" in out
+    mix = [l for l in out.splitlines() if l.startswith("#   ")]
+    assert mix[0].split()[1] == "FFMA" and any(l.split()[1] == "BRA" and "10.0 %" in l for l in mix)
+    assert sum("UBLKCP.S.G" in l for l in out.splitlines() if l.startswith("  [")) == 1
+    win = out.split("(3)")[1].splitlines()[1:]
+    assert len(win) == 2 and "BRA" in win[0] and "MUFU.EX2" in win[1]

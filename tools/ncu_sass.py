@@ -20,11 +20,11 @@ for r in csv.reader(open(a.csv)):
     if r and r[0] == "Address":
         hdr = r
         continue
-    if hdr is None or len(r) < 8:
+    if hdr is None:
         continue
     try:
         ins.append((r[1].strip(), int(r[hdr.index("Instructions Executed")]), int(r[hdr.index("# Samples")])))
-    except ValueError:
+    except (ValueError, IndexError):
         pass
 tot, smp = sum(i[1] for i in ins), sum(i[2] for i in ins)
 if a.title:

@@ -1,6 +1,9 @@
 """CPU analysis of the compositing workload of one bench view (no GPU): from the oracle's per-tile lists,
 count what a 16x16-pixel tile kernel has to evaluate -- list entries walked per pixel until the reference's
-stop rule, entries a 16x2 warp strip can skip, live lanes per visited entry.  Test/analysis tooling: uses
+stop rule, entries a 16x2 warp strip can skip, live lanes per visited entry -- and, per candidate shape of the
+pixel block a warp owns (--shapes), how many power evaluations and blend evaluations a pixel pays when a warp
+skips an entry only if none of its pixels is live: the count behind composite_kernel's 8x8 warp blocks (16x4
+strips: 70.2 / 64.5 per pixel, 8x8 blocks: 68.3 / 60.4, really blended: 51.1).  Test/analysis tooling: uses
 oracle/ (allowed for tools that are neither product nor bench legs)."""
 import argparse
 import os
@@ -20,7 +23,11 @@ def main():
     ap.add_argument("--W", type=int, default=512)
     ap.add_argument("--H", type=int, default=512)
     ap.add_argument("--tiles", type=int, default=128, help="number of tiles sampled")
+    ap.add_argument("--shapes", default="16x4,8x8,16x2,8x4,16x16", help="warp pixel blocks (width x height) to compare")
     a = ap.parse_args()
+    shapes = {k: (int(k.split("x")[1]), int(k.split("x")[0])) for k in a.shapes.split(",") if k}
+    blocks = lambda m, bh, bw: m.reshape(16 // bh, bh, 16 // bw, bw).transpose(0, 2, 1, 3).reshape(-1, bh * bw)
+    shape_tot = {k: [0, 0] for k in shapes}   # pixel-evaluations of power, of exp + blend
     g = synth.make_gaussians(1234, a.P)
     cam = synth.make_camera(a.W, a.H, "side", jitter_seed=1)
     col, rad, dep, aux = raster_ref.rasterize(g.means3D, g.opacities, viewmatrix=cam.view, projmatrix=cam.proj,
@@ -58,6 +65,9 @@ def main():
                 continue
             tot["kept"] += 1
             live = vis & ~done
+            for k, (bh, bw) in shapes.items():         # a warp evaluates power unless all its pixels are done,
+                shape_tot[k][0] += int((~blocks(done, bh, bw).all(1)).sum()) * bh * bw
+                shape_tot[k][1] += int(blocks(live, bh, bw).any(1).sum()) * bh * bw   # and blends if any is live
             wl = live.reshape(8, 32).any(1)            # 16x2 strips = rows (2k, 2k+1)
             wd = done.reshape(8, 32).all(1)
             tot["warp_visit"] += int((~wd).sum())
@@ -79,6 +89,10 @@ def main():
     print(f"  lane-live {tot['lane_live'] / n:.0f}, lane-blend {tot['lane_blend'] / n:.0f}, "
           f"not-done pixel visits {tot['pix_walk'] / n:.0f}")
     print(f"  lanes live per live warp {tot['lane_live'] / max(1, tot['warp_live']):.1f} / 32")
+    npx = 256.0 * n
+    print(f"per pixel: live {tot['lane_live'] / npx:.1f}, blended {tot['lane_blend'] / npx:.1f}; by warp pixel block:")
+    for k, (pw, bl) in shape_tot.items():
+        print(f"  {k:6s} power evaluations {pw / npx:5.1f}  blend evaluations {bl / npx:5.1f}")
 
 
 if __name__ == "__main__":

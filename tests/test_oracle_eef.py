@@ -121,3 +121,20 @@ def test_known_answers():
     assert eef_ref.hysteresis(0.2, 0.5, True, small, faces, 3e4)[2:] == (float(np.float32(0.2)), False)
     mid = np.full((6, 3), 100.0, np.float32)   # |sum| ~ 520: neither small nor large
     assert eef_ref.hysteresis(0.2, 0.5, True, mid, faces, 3e4) == (0.45, 0.5, 0.45, True)
+
+
+def test_restated_kornia_axis_angle_agrees_with_scipy():
+    """kornia is not installable here, so `axis_angle_to_rotation_matrix` is restated from its published algorithm
+    (parity unpinned).  scipy's Rotation.from_rotvec is an independent implementation of the same map: the restated
+    function equals it to 3e-6 over rotation angles from 1e-5 rad (the first-order branch, theta^2 <= 1e-6) to pi --
+    what is left unpinned is kornia's `+ 1e-6` in the axis normalisation and its branch threshold, both restated."""
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(3)
+    axis = rng.normal(size=(3000, 3))
+    axis /= np.linalg.norm(axis, axis=1, keepdims=True)
+    theta = np.concatenate([10 ** rng.uniform(-5, -3, 1000), rng.uniform(1e-3, 0.05, 1000), rng.uniform(0.05, np.pi, 1000)])
+    aa = (axis * theta[:, None]).astype(np.float32)
+    R = eef_ref.axis_angle_to_rotation_matrix(aa)
+    want = Rotation.from_rotvec(aa.astype(np.float64)).as_matrix()
+    assert np.abs(R - want).max() < 3e-6
+    assert (theta ** 2 <= 1e-6).sum() > 100 and (theta ** 2 > 1e-6).sum() > 100, "both branches exercised"

@@ -65,3 +65,21 @@ def test_known_answers():
                        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
                        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
         assert np.abs(R - R2).max() < 1e-5
+
+
+def test_restated_kornia_quaternion_agrees_with_scipy():
+    """kornia is not installable here, so `rotation_matrix_to_quaternion` is restated from its published four-branch
+    algorithm (parity unpinned).  An independent implementation narrows what is unpinned to kornia's branch choice and
+    its eps: scipy's Rotation.from_matrix gives the same rotation (as (x, y, z, w), up to the overall sign) on random
+    rotations that exercise all four branches, to 2e-6."""
+    from scipy.spatial.transform import Rotation
+    rot = Rotation.random(4000, random_state=7)
+    R = rot.as_matrix().astype(np.float32)
+    q = links_ref.rotation_matrix_to_quaternion(R)                       # (w, x, y, z)
+    tr = R[:, 0, 0] + R[:, 1, 1] + R[:, 2, 2]
+    d = np.stack([R[:, 0, 0], R[:, 1, 1], R[:, 2, 2]], 1)
+    assert (tr > 0).any() and all(((tr <= 0) & (d.argmax(1) == k)).any() for k in range(3)), "all four branches hit"
+    s = Rotation.from_matrix(R.astype(np.float64)).as_quat()[:, [3, 0, 1, 2]]
+    sign = np.sign((q * s).sum(1, keepdims=True))
+    assert np.abs(q * sign - s).max() < 2e-6
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-6

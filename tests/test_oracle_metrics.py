@@ -67,3 +67,22 @@ def test_known_answers():
     passed = [True] * 10 + [False] * 5 + [True] * 40
     out = metrics_ref.episode_rule(passed, start_frame=12, need=30)
     assert out[11] == (0, False) and out[15 + 28] == (29, False) and out[15 + 29] == (30, True) and out[-1][1]
+
+
+def test_restated_obb_rule_agrees_with_a_convex_hull_test():
+    """Open3D is not installable here, so its point-in-oriented-box rule (the sloth success test) is restated (parity
+    unpinned).  An independent geometric test -- membership in the convex hull of the box's eight corners, by
+    scipy's Delaunay triangulation -- selects the same points wherever a point is not within 1e-9 of a face."""
+    from scipy.spatial import Delaunay
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(12)
+    R = Rotation.random(random_state=5).as_matrix()
+    center, extent = np.array([0.31, -0.12, 0.07]), np.array([0.20, 0.11, 0.06])
+    x = center + rng.uniform(-0.16, 0.16, (20000, 3))
+    corners = center + (np.array([[sx, sy, sz] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)]) * extent / 2) @ R.T
+    hull = Delaunay(corners)
+    inside_hull = hull.find_simplex(x) >= 0
+    local = np.abs((x - center) @ R) - extent / 2
+    clear = np.abs(local).min(1) > 1e-9                       # not on a face, where the two tests may round differently
+    n = metrics_ref.obb_count(x[clear], center, R, extent)
+    assert n == int(inside_hull[clear].sum()) and 200 < n < 19000

@@ -104,3 +104,58 @@ def test_mesh_query_contract():
     assert q.result and q.face == 0 and q.sign == F32(1.0) and np.allclose(p, [0.2, 0.2, 0.0], atol=1e-7)
     q = wp.mesh_query_point_sign_winding_number(m.id, wp.vec3(0.2, 0.2, 0.01), max_dist=0.02, accuracy=3.0, threshold=0.6)
     assert q.result and q.face == 0 and q.sign == F32(-1.0), "inside: winding number ~1 > threshold"
+
+
+def test_restated_mesh_query_agrees_with_independent_geometry():
+    """warp-lang's native library is not available, so `mesh_query_point_sign_winding_number` is restated (parity
+    unpinned).  Independent geometry narrows what is unpinned to Warp's tie rule and its far-field approximation: on
+    the closed finger mesh the restated query returns the minimum over the triangles of a closest distance computed
+    another way (plane projection if it falls inside the triangle, else the nearest of the three edge segments --
+    not Ericson's region walk), and its inside / outside sign equals ray-casting parity."""
+    from real2sim_eval_b200 import synth
+    g = synth.make_gripper(center=(0.0, 0.0, 0.0), gap=0.03)
+    v, f = g.verts[:24].astype(np.float64), g.faces[:44]            # the left finger: a closed 44-triangle box
+    m = wp.Mesh(points=wp.array(g.verts[:24], dtype=wp.vec3), indices=wp.array(f.reshape(-1).astype(np.int32), dtype=int))
+    rng = np.random.default_rng(21)
+    lo, hi = v.min(0) - 0.01, v.max(0) + 0.01
+    pts = rng.uniform(lo, hi, (300, 3))
+
+    def seg(p, a, b):
+        t = np.clip(np.dot(p - a, b - a) / np.dot(b - a, b - a), 0.0, 1.0)
+        return np.linalg.norm(p - (a + t * (b - a)))
+
+    def tri_dist(p, a, b, c):
+        n = np.cross(b - a, c - a)
+        n /= np.linalg.norm(n)
+        q = p - np.dot(p - a, n) * n
+        inside = all(np.dot(np.cross(e1 - e0, q - e0), n) >= 0 for e0, e1 in ((a, b), (b, c), (c, a)))
+        return abs(np.dot(p - a, n)) if inside else min(seg(p, a, b), seg(p, b, c), seg(p, c, a))
+
+    def inside_by_parity(p):
+        d = np.array([0.3713, 0.5821, 0.7233])                       # generic direction: no edge or vertex hits
+        hits = 0
+        for a, b, c in v[f]:
+            e1, e2 = b - a, c - a
+            h = np.cross(d, e2)
+            det = np.dot(e1, h)
+            if abs(det) < 1e-15:
+                continue
+            s = p - a
+            u = np.dot(s, h) / det
+            q = np.cross(s, e1)
+            w = np.dot(d, q) / det
+            hits += int(u >= 0 and w >= 0 and u + w <= 1 and np.dot(e2, q) / det > 0)
+        return hits % 2 == 1
+
+    n_in = 0
+    for p in pts:
+        q = wp.mesh_query_point_sign_winding_number(m.id, wp.vec3(*p.astype(np.float32)), max_dist=1.0, accuracy=3.0,
+                                                    threshold=0.6)
+        assert q.result
+        hit = np.asarray(wp.mesh_eval_position(m.id, q.face, q.u, q.v), np.float64)
+        want = min(tri_dist(p, *v[t]) for t in f)
+        assert abs(np.linalg.norm(p.astype(np.float32) - hit) - want) < 2e-6
+        inside = inside_by_parity(p)
+        assert (q.sign < 0) == inside
+        n_in += inside
+    assert 20 < n_in < 280, "points on both sides of the surface"

@@ -110,9 +110,10 @@ typedef struct r2s_raster_layout {
     size_t depths;       /* float  [B*P]  view-space z                                */
     size_t radii;        /* int32  [B*P]                                             */
     size_t tiles_touched; /* uint32 [B*P]                                            */
-    size_t rec_a;        /* float4 [B*P] {x, y, conic.x, conic.y}                     */
-    size_t rec_b;        /* float4 [B*P] {conic.z, opacity, r, g}                     */
-    size_t rec_c;        /* float  [B*P] {b}                                          */
+    size_t rec_a;        /* float4 [B*P][2]: one 32-byte record per Gaussian, {x, y, conic.x, conic.y} then
+                            {conic.z, opacity, r, g} -- a visible Gaussian writes exactly one DRAM sector  */
+    size_t rec_b;        /* = rec_a + 16: the second float4 of record 0 (stride 32 bytes)               */
+    size_t rec_c;        /* float  [B*P] {b} (0 for culled Gaussians: written densely)                  */
     size_t rects;        /* uint32 [B*P] tile rectangle minx | miny<<8 | maxx<<16 | maxy<<24 (0 = culled) */
     size_t tile_count;   /* uint32 [B*ST] instances per super-tile (4x4 tiles)          */
     size_t tile_offset;  /* uint32 [B*ST+1] exclusive scan; list[s] = keys[off[s] .. off[s+1]) */

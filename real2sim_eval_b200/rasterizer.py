@@ -186,8 +186,8 @@ class BatchedRasterizer:
             depths=view(L.depths, 4 * B * P, torch.float32).view(B, P),
             radii=view(L.radii, 4 * B * P, torch.int32).view(B, P),
             tiles_touched=view(L.tiles_touched, 4 * B * P, torch.int32).view(B, P),
-            rec_a=view(L.rec_a, 16 * B * P, torch.float32).view(B, P, 4),
-            rec_b=view(L.rec_b, 16 * B * P, torch.float32).view(B, P, 4),
+            rec_a=view(L.rec_a, 32 * B * P, torch.float32).view(B, P, 8)[..., :4],   # 32-byte records {rec_a, rec_b}
+            rec_b=view(L.rec_a, 32 * B * P, torch.float32).view(B, P, 8)[..., 4:],
             rec_c=view(L.rec_c, 4 * B * P, torch.float32).view(B, P),
             rects=view(L.rects, 4 * B * P, torch.int32).view(B, P),
             super_count=view(L.tile_count, 4 * B * T, torch.int32).view(B, T),

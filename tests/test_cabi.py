@@ -79,10 +79,11 @@ def test_workspace_layout_arithmetic():
     L = _lib.RasterLayout()
     assert lib.r2s_raster_workspace_layout(4, 1000, 512, 480, 50000, C.byref(L)) == 0
     assert (L.tiles_x, L.tiles_y, L.super_x, L.super_y) == (32, 30, 8, 8)
-    offs = [L.status, L.depths, L.radii, L.tiles_touched, L.rec_a, L.rec_b, L.rec_c, L.rects, L.tile_count,
+    offs = [L.status, L.depths, L.radii, L.tiles_touched, L.rec_a, L.rec_c, L.rects, L.tile_count,
             L.tile_offset, L.tile_fill, L.keys, L.keys_alt, L.sorted_rect, L.total]
     assert offs == sorted(offs) and all(o % 256 == 0 for o in offs[:-1])
-    assert L.rec_b - L.rec_a >= 16 * 4 * 1000 and L.keys_alt - L.keys >= 8 * 50000
+    assert L.rec_b == L.rec_a + 16 and L.rec_c - L.rec_a >= 32 * 4 * 1000, "32-byte records {rec_a, rec_b}"
+    assert L.keys_alt - L.keys >= 8 * 50000
     assert lib.r2s_raster_workspace_bytes(4, 1000, 512, 480, 50000) == L.total
     assert lib.r2s_raster_workspace_layout(1, 10, 16 * 300, 64, 10, C.byref(L)) != 0, "tile rectangles are 8-bit"
     assert lib.r2s_raster_workspace_bytes(0, 10, 64, 64, 10) == 0

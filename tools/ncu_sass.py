@@ -18,6 +18,8 @@ a = ap.parse_args()
 hdr, ins = None, []
 for r in csv.reader(open(a.csv)):
     if r and r[0] == "Address":
+        if hdr is not None:   # the page lists the kernel once per source view: keep the first listing
+            break
         hdr = r
         continue
     if hdr is None:

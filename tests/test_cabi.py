@@ -107,3 +107,26 @@ def test_product_path_has_no_cpu_fallback_and_never_imports_the_oracle():
     code = "import sys, real2sim_eval_b200, real2sim_eval_b200.physics, real2sim_eval_b200.rasterizer, " \
            "real2sim_eval_b200.envs; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_preprocess_fp_pairing_signature_is_the_one_verified_on_the_gpu():
+    """preprocess_kernel is bit-identical to the reference build only while ptxas fuses the same multiplies with the
+    same adds (moving loads or changing the register cap has changed conics / SH colours by an ulp
+    before).  tests/golden/sass_signature_preprocess.json holds the floating-point instruction signature of the build
+    whose images were `array_equal` to the live reference on a B200; a different signature from the same toolchain
+    means: re-run `pytest -m gpu tests/test_gpu_raster.py`, then refresh the file with tools/sass_signature.py --write."""
+    import json
+    import shutil
+    from real2sim_eval_b200 import _lib
+    root = ROOT
+    sys.path.insert(0, os.path.join(root, "tools"))
+    import sass_signature
+    _lib.load()   # builds the library if needed
+    if not (shutil.which("cuobjdump") or os.path.exists("/usr/local/cuda/bin/cuobjdump")):
+        pytest.skip("cuobjdump not available")
+    want = json.load(open(os.path.join(root, "tests", "golden", "sass_signature_preprocess.json")))
+    if sass_signature.toolchain() != want["nvcc"]:
+        pytest.skip(f"signature recorded with nvcc {want['nvcc']}")
+    got = sass_signature.signature(_lib.LIB_PATH, "preprocess_kernel")
+    assert got["by_opcode"] == want["by_opcode"] and got["digest"] == want["digest"], \
+        "FP instruction pairing of preprocess_kernel changed: re-verify bit-identity on a GPU, then refresh the golden"

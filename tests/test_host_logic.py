@@ -268,3 +268,42 @@ def test_ncu_sass_tool_summarises_a_source_page(tmp_path):
     assert sum("UBLKCP.S.G" in l for l in out.splitlines() if l.startswith("  [")) == 1
     win = out.split("(3)")[1].splitlines()[1:]
     assert len(win) == 2 and "BRA" in win[0] and "MUFU.EX2" in win[1]
+
+
+def test_exponent_field_arithmetic_of_the_compositing_kernel():
+    """The IEEE facts raster.cu's opacity_expf_seq rests on, checked in numpy float32 (no GPU):
+    (1) expf's range reduction t = floor(252 * s + magic) keeps the biased exponent j + 127 in its low bits; with the
+        magic lowered by 127 the low 9 bits of t's bit pattern are j itself in two's complement, and t - 12582912 == j;
+    (2) fl(op * (2^j * r)) == fl(op * r) scaled by 2^j (an integer add of j << 23 on the bit pattern) whenever the
+        product stays normal -- which holds wherever an entry can be blended: op * e^x >= 0.998/255;
+    (3) below power_min = -log(255 * op) - 2e-3 the alpha of forward.cu:350 is below 1/255, so the warp vote may skip."""
+    rng = np.random.default_rng(8)
+    f32 = np.float32
+    # (1): fma.rm to a float32 in [2^23, 2^24) is floor() of the exact value; 252 * s + magic is exact in float64
+    s = rng.uniform(0, 1, 20000).astype(f32)
+    s[:2] = [0.0, 1.0]
+    t_lib = np.floor(252.0 * s.astype(np.float64) + 12582913.0).astype(f32)        # libdevice's constant
+    t_new = np.floor(252.0 * s.astype(np.float64) + 12582786.0).astype(f32)        # lowered by 127
+    j = (t_lib - f32(12583039.0)).astype(np.int64)
+    assert np.array_equal((t_new - f32(12582912.0)).astype(np.int64), j) and j.min() == -126 and j.max() == 126
+    assert np.array_equal(t_lib.view(np.uint32) & 0xFF, (j + 127).astype(np.uint32)), "libdevice: biased exponent in the low byte"
+    assert np.array_equal(t_new.view(np.uint32) & 0x1FF, (j % 512).astype(np.uint32)), "lowered magic: j in two's complement"
+    assert np.array_equal(((t_new.view(np.uint32).astype(np.uint64) << 23) & 0xFFFFFFFF).astype(np.uint32),
+                          ((j.astype(np.int64) << 23) & 0xFFFFFFFF).astype(np.uint32))
+    # (2): scaling by 2^j commutes with the rounding of op * r while nothing underflows
+    n = 200000
+    op = np.concatenate([rng.uniform(1e-3, 1.0, n // 2), 10 ** rng.uniform(-2.4, 0.6, n // 2)]).astype(f32)
+    r = rng.uniform(0.7, 1.4143, n).astype(f32)                                    # ex2 of the reduced argument
+    jj = rng.integers(-9, 1, n)
+    two_j = np.ldexp(f32(1.0), jj).astype(f32)
+    ref = op * (two_j * r)                                                         # fmul(opacity, expf(x))
+    live = ref >= f32(0.998 / 255.0)
+    bits = (op * r).view(np.uint32).astype(np.int64) + (jj.astype(np.int64) << 23)
+    got = (bits & 0xFFFFFFFF).astype(np.uint32).view(f32)
+    assert live.sum() > n // 3 and np.array_equal(got[live], ref[live])
+    # (3): the lower bound of the warp vote
+    opv = 10 ** rng.uniform(-2.3, 0.5, 50000)
+    pmin = (-np.log(255.0 * opv) - 2e-3).astype(f32)
+    x = (pmin - np.abs(rng.normal(0, 0.5, opv.size)).astype(f32) - f32(1e-6)).astype(f32)     # just below the bound and further down
+    alpha = np.minimum(f32(0.99), opv.astype(f32) * np.exp(x.astype(f32)))
+    assert (alpha < f32(1.0 / 255.0)).all()
